@@ -1,0 +1,250 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI of
+libturbosqueeze_b200.so; the oracle (tests/oraclelib.py) is only the checker.
+
+Bar: bit-exact.  encode: every byte of every block's stream equals the reference's (oracle/_ref when
+it travelled with the repo, else the pinned C restatement) under the contract of SURVEY.md 8(c);
+decode: output equals the original input.
+"""
+import ctypes as C
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oraclelib import PAD, Reference, slot_stride
+from turbosqueeze_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden_blocks.json")))
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+@pytest.fixture(scope="module")
+def ctx(torch):
+    import turbosqueeze_b200 as T
+    c = T.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def checker(oracle):
+    """The compiled unmodified reference when present (multi-threaded), else the C restatement."""
+    return Reference() if Reference.available() else oracle
+
+
+def gpu_encode(torch, ctx, buf, n, block, ext, impl):
+    import turbosqueeze_b200 as T
+    assert T.slot_stride(block) == slot_stride(block)
+    ctx.set_option("encode_impl", impl)
+    d = torch.from_numpy(buf).cuda()
+    slots, sizes = ctx.encode_blocks(d, n, block, ext)
+    torch.cuda.synchronize()
+    return slots.cpu().numpy(), sizes.cpu().numpy().astype(np.uint32)
+
+
+def assert_streams_equal(a_slots, a_sizes, b_slots, b_sizes, block, what):
+    assert np.array_equal(a_sizes, b_sizes), (what, "sizes differ", np.flatnonzero(a_sizes != b_sizes)[:5])
+    stride = slot_stride(block)
+    nb = len(a_sizes)
+    if nb * stride <= (1 << 28):
+        idx = np.arange(stride, dtype=np.int64)[None, :] < a_sizes.astype(np.int64)[:, None]
+        A = a_slots[: nb * stride].reshape(nb, stride)
+        B = b_slots[: nb * stride].reshape(nb, stride)
+        bad = np.flatnonzero(((A != B) & idx).any(axis=1))
+        assert bad.size == 0, (what, "blocks differ", bad[:5])
+    else:
+        for b in range(nb):
+            s = int(a_sizes[b])
+            assert np.array_equal(a_slots[b * stride: b * stride + s], b_slots[b * stride: b * stride + s]), (what, "block", b)
+
+
+def golden_input(g):
+    n = g["n"]
+    if g["input_kind"] == "literal-bytes":
+        buf = np.zeros(n + PAD, dtype=np.uint8)
+        buf[:n] = np.frombuffer(bytes.fromhex(g["input_hex"]), dtype=np.uint8)
+    elif g["input_kind"] == "zeros":
+        buf = np.zeros(n + PAD, dtype=np.uint8)
+    else:
+        buf = W.fill(g["input_kind"], n, seed=g["seed"])
+    return buf
+
+
+@pytest.mark.parametrize("impl,ext", [(2, 0), (1, 0), (1, 1)], ids=["warp", "scalar", "scalar-ext"])
+def test_encode_matches_reference_golden_vectors(torch, ctx, impl, ext):
+    """tests/golden/golden_blocks.json was produced by the compiled unmodified reference."""
+    for g in GOLDEN:
+        buf = golden_input(g)
+        e = g["ext" if ext else "noext"]
+        slots, sizes = gpu_encode(torch, ctx, buf, g["n"], g["block"], ext, impl)
+        stride = slot_stride(g["block"])
+        assert len(sizes) == e["n_blocks"], g["name"]
+        assert [int(s) for s in sizes[:8]] == e["sizes_head"], g["name"]
+        assert int(sizes.sum()) == e["sizes_sum"], g["name"]
+        h = hashlib.sha256()
+        for b, s in enumerate(sizes):
+            h.update(slots[b * stride: b * stride + int(s)].tobytes())
+        if "hex" in e:
+            assert slots[: int(sizes[0])].tobytes().hex() == e["hex"], g["name"]
+        assert h.hexdigest() == e["sha256"], g["name"]
+
+
+CASES = [(1, 1), (2, 2), (5, 5), (31, 31), (32, 32), (33, 33), (34, 34), (63, 64), (100, 100), (4096, 4096), (65535, 65535),
+         (65536, 65536), (65537, 65537), (70000, 70000), (200000, 65536), (1 << 20, 4096), (1 << 20, 1000), (3 << 20, 262144),
+         ((3 << 20) + 12345, 262144), ((4 << 20) + 1, 1 << 22), (600000, 131072 + 7)]
+
+
+@pytest.mark.parametrize("kind", ["text", "random", "rep8", "zeros", "runs"])
+@pytest.mark.parametrize("impl,ext", [(2, 0), (1, 0), (1, 1)], ids=["warp", "scalar", "scalar-ext"])
+def test_encode_bit_exact_vs_oracle(torch, ctx, checker, kind, impl, ext):
+    rng = np.random.default_rng(11)
+    cases = CASES + [(int(rng.integers(1, 400000)), int(rng.integers(1, 300000))) for _ in range(6)]
+    for n, block in cases:
+        buf = make_input(kind, n, seed=n + 3)
+        want_slots, want_sizes, _ = checker.encode_blocks(buf, n, block, ext)
+        got_slots, got_sizes = gpu_encode(torch, ctx, buf, n, block, ext, impl)
+        assert_streams_equal(got_slots, got_sizes, want_slots, want_sizes, block, (kind, n, block, impl, ext))
+
+
+def make_input(kind, n, seed):
+    if kind == "zeros":
+        return np.zeros(n + PAD, dtype=np.uint8)
+    if kind == "runs":   # short runs and near repeats: stresses same-hash positions inside one 32-wide window
+        rng = np.random.default_rng(seed)
+        sym = rng.integers(97, 101, size=n // 3 + 2, dtype=np.uint8)
+        a = np.repeat(sym, rng.integers(1, 9, size=sym.size))[:n]
+        buf = np.zeros(n + PAD, dtype=np.uint8)
+        buf[: a.size] = a
+        if a.size < n:
+            buf[a.size:n] = 120
+        return buf
+    return W.fill(kind, n, seed=seed)
+
+
+@pytest.mark.parametrize("lanes", [32, 16, 8, 4, 2, 1])
+@pytest.mark.parametrize("ext", [0, 1])
+def test_decode_restores_input(torch, ctx, oracle, lanes, ext):
+    ctx.set_option("decode_lanes", lanes)
+    try:
+        for kind in ("text", "random", "rep8", "zeros", "runs"):
+            for n, block in [(1, 1), (5, 5), (100, 100), (4096, 4096), (70000, 70000), (200000, 65536), (1 << 20, 4096),
+                             ((3 << 20) + 12345, 262144), ((4 << 20) + 1, 1 << 22)]:
+                buf = make_input(kind, n, seed=n + 5)
+                slots, sizes, _ = oracle.encode_blocks(buf, n, block, ext)
+                nb = len(sizes)
+                d_slots = torch.from_numpy(slots).cuda()
+                d_sizes = torch.from_numpy(sizes.astype(np.int32)).cuda()
+                out, osz = ctx.decode_blocks(d_slots, nb, block, ext, comp_sizes=d_sizes)
+                torch.cuda.synchronize()
+                osz = osz.cpu().numpy()
+                assert int(osz.sum()) == n, (kind, n, block)
+                assert np.array_equal(out.cpu().numpy()[:n], buf[:n]), (kind, n, block, lanes, ext)
+    finally:
+        ctx.set_option("decode_lanes", 0)
+
+
+def test_decode_rejects_oversize_header(torch, ctx):
+    """tsq_decode.cpp:53 -- header size > 4 MiB => outputSize 0 (and nothing written)."""
+    import turbosqueeze_b200 as T
+    assert T.tsqDecode(bytes([0x01, 0x00, 0x40]) + bytes(32)) == b""
+    assert T.tsqDecode(bytes([0x00, 0x00, 0x00]) + bytes(32)) == b""
+
+
+def test_reference_block_api_round_trip(torch, checker):
+    """Mirror of the reference's test_tsq_compress (test/test.cpp:30-54) through tsqEncode/tsqDecode,
+    plus byte equality with the reference for both formats and for a non-zero pre-filled output."""
+    import turbosqueeze_b200 as T
+    g = next(x for x in GOLDEN if x["name"] == "testinput_699")
+    data = bytes.fromhex(g["input_hex"])
+    for ext in (0, 1):
+        stream = T.tsqEncode(data, ext)
+        assert stream.hex() == g["ext" if ext else "noext"]["hex"]
+        assert T.tsqDecode(stream, ext) == data
+    # trailing never-initialised bytes follow the caller's pre-fill
+    if isinstance(checker, Reference):
+        rng = np.random.default_rng(3)
+        for n in (16, 64, 128, 1000, 4096, 65536):
+            raw = rng.integers(0, 256, size=n, dtype=np.uint8)
+            buf = np.zeros(n + PAD, dtype=np.uint8); buf[:n] = raw
+            for fill in (0x00, 0xAB):
+                pre = np.full(slot_stride(n), fill, dtype=np.uint8)
+                slots, sizes, _ = checker.encode_blocks(buf, n, n, 0, slots=pre, zero=False)
+                assert T.tsqEncode(raw, 0, prefill=fill) == slots[: int(sizes[0])].tobytes(), (n, fill)
+
+
+def test_tail_bytes_are_read_like_the_reference(torch, ctx, checker):
+    """the bytes after a block influence its stream."""
+    import turbosqueeze_b200 as T
+    n = 50000
+    buf = W.fill("text", n + 64, seed=9)
+    follow = buf.copy(); follow[n + 64:] = 0
+    want_slots, want_sizes, _ = checker.encode_blocks(follow, n, n, 0)
+    got = T.tsqEncode(buf[:n], 0, tail=buf[n:n + 64])
+    assert got == want_slots[: int(want_sizes[0])].tobytes()
+
+
+def test_container_pack_index_and_buffer_api(torch, ctx, oracle):
+    """TSQ1 framing on the device + the synchronous buffer API (tsq_threads.cpp:413-441,862-890)."""
+    import turbosqueeze_b200 as T
+    for ext in (0, 1):
+        for n, block in [(1, 4096), (5000, 4096), ((5 << 20) + 321, 1 << 22), (1 << 20, 65536)]:
+            buf = W.fill("text", n, seed=77)
+            blob = ctx.compress_buffer(buf[:n], block, ext)
+            nb = (n + block - 1) // block
+            assert blob[:4] == b"TSQ1" and int.from_bytes(blob[4:8], "little") == nb
+            assert int.from_bytes(blob[8:16], "little") == n
+            # walk the container on the host: every block equals the oracle's stream
+            slots, sizes, _ = oracle.encode_blocks(buf, n, block, ext)
+            stride = slot_stride(block)
+            at = 16
+            for b in range(nb):
+                ln = int.from_bytes(blob[at:at + 3], "little"); at += 3
+                assert bool(ln & 0x800000) == bool(ext)
+                ln &= 0x7FFFFF
+                assert ln == int(sizes[b])
+                assert blob[at:at + ln] == slots[b * stride: b * stride + ln].tobytes()
+                at += ln
+            assert at == len(blob)
+            assert ctx.decompress_buffer(blob) == buf[:n].tobytes()
+    # reference-style MT buffer API, memory -> memory (test/test.cpp:149-199)
+    n = (9 << 20) + 77
+    buf = W.fill("text", n, seed=5)
+    for ext in (0, 1):
+        blob = T.tsq_compress_mt(buf[:n], ext)
+        assert blob is not None and T.tsq_decompress_mt(blob) == buf[:n].tobytes()
+    if Reference.available():
+        ref = Reference()
+        blob = T.tsq_compress_mt(buf[:n], 0)
+        assert ref.decompress_mt(blob) == buf[:n].tobytes()           # the reference reads our container
+        assert T.tsq_decompress_mt(ref.compress_mt(buf[:n], 1)) == buf[:n].tobytes()   # and we read its
+
+
+@pytest.mark.parametrize("kind,block", [("text", 262144), ("random", 262144), ("rep8", 1 << 20), ("text", 4096)])
+def test_large_buffers_bit_exact_and_round_trip(torch, ctx, checker, kind, block):
+    """BASELINE.json shapes at a size the multi-threaded reference finishes in seconds (256 MiB):
+    every stream byte equals the reference's, and decode(encode(x)) == x on the device."""
+    n = (256 << 20) + 54321
+    buf = W.fill(kind, n, seed=2024)
+    ctx.set_option("encode_impl", 0)
+    d = torch.from_numpy(buf).cuda()
+    slots, sizes = ctx.encode_blocks(d, n, block, 0)
+    out, osz = ctx.decode_blocks(slots, sizes.numel(), block, 0, comp_sizes=sizes)
+    torch.cuda.synchronize()
+    assert int(osz.sum().item()) == n
+    assert torch.equal(out[:n], d[:n])
+    threads = os.cpu_count() or 8
+    want_slots, want_sizes, _ = checker.encode_blocks(buf, n, block, 0, threads=threads)
+    got_sizes = sizes.cpu().numpy().astype(np.uint32)
+    assert np.array_equal(got_sizes, want_sizes)
+    assert_streams_equal(slots.cpu().numpy(), got_sizes, want_slots, want_sizes, block, (kind, block))

@@ -1,0 +1,581 @@
+// tsq_capi.cu -- the C-ABI of libturbosqueeze_b200.so (include/tsq_b200.h).
+//
+// Layer 1 (tsqb_*) launches the kernels on device-resident buffers.  Layer 2 re-implements the
+// reference's entry points (reference turbosqueeze.h:458-670) as host wrappers around layer 1:
+// stage H2D, launch, copy back.  No CPU codec exists in this library: without a CUDA device every
+// call fails.
+#include "../../include/tsq_b200.h"
+#include "tsq_device.cuh"
+
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace tsqb;
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int fail(const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) return fail("%s: %s", #call, cudaGetErrorString(e_));              \
+    } while (0)
+
+extern "C" const char* tsqb_last_error(void) { return g_err.c_str(); }
+
+extern "C" int tsqb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ----------------------------------------------------------------------------------------- context
+struct DevBuf {
+    void*  p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        const size_t want = (n + (1u << 20)) & ~(size_t)((1u << 20) - 1);
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return 1; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct tsqb_context {
+    int device = 0;
+    int sm_count = 148;
+    int encode_impl = 0;       // 0 auto, 1 scalar, 2 warp
+    int decode_lanes = 0;      // 0 auto
+    int64_t encode_slots = 0;  // 0 auto
+    DevBuf tables;             // hash tables of the blocks in flight
+    // staging for the host-buffer entry points
+    DevBuf in, slots, sizes, out, osizes, cont, offs, ext, misc;
+    cudaStream_t stream = nullptr;
+    std::mutex mtx;
+};
+
+extern "C" int tsqb_create(tsqb_context** out, int device)
+{
+    if (!out) return fail("tsqb_create: null out pointer");
+    *out = nullptr;
+    const int n = tsqb_device_count();
+    if (n <= 0) return fail("tsqb_create: no CUDA device available (this library has no CPU path)");
+    if (device < 0 || device >= n) return fail("tsqb_create: device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    tsqb_context* c = new tsqb_context();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        return fail("tsqb_create: cudaStreamCreate failed");
+    }
+    *out = c;
+    g_err.clear();
+    return 0;
+}
+
+extern "C" void tsqb_destroy(tsqb_context* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (DevBuf* b : {&c->tables, &c->in, &c->slots, &c->sizes, &c->out, &c->osizes, &c->cont, &c->offs, &c->ext, &c->misc})
+        b->release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" uint64_t tsqb_slot_stride(uint32_t block)
+{
+    const uint64_t n = 5ull + block + (block >> 4) + ((block + 15u) >> 4) + 32u;
+    return (n + 127u) / 128u * 128u;
+}
+
+extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
+{
+    if (!c || !key) return 1;
+    if (!strcmp(key, "encode_impl"))  { c->encode_impl = (int)v; return 0; }
+    if (!strcmp(key, "decode_lanes")) { c->decode_lanes = (int)v; return 0; }
+    if (!strcmp(key, "encode_slots")) { c->encode_slots = v; return 0; }
+    return 1;
+}
+
+// ------------------------------------------------------------------------------ layer 1: device path
+static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t total, uint32_t block, uint8_t* d_slots,
+                              uint64_t stride, uint32_t* d_sizes, uint32_t* d_tailflags, uint32_t with_ext, void* stream)
+{
+    if (!c) return fail("tsqb_encode_blocks: null context");
+    if (block == 0 || block > kBlockMax) return fail("tsqb_encode_blocks: block size %u not in 1..%u", block, kBlockMax);
+    if (stride < tsqb_slot_stride(block)) return fail("tsqb_encode_blocks: slot stride %llu < %llu", (unsigned long long)stride,
+                                                      (unsigned long long)tsqb_slot_stride(block));
+    if (total == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    EncodeArgs a;
+    a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
+    a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
+    const int impl = (c->encode_impl == 1 || with_ext) ? 1 : 2;
+    a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
+    if (c->tables.ensure((size_t)a.n_slots * kTableBytes)) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
+    a.tables = (uint16_t*)c->tables.p;
+    CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int tsqb_encode_blocks(tsqb_context* c, const uint8_t* d_in, uint64_t total, uint32_t block, uint8_t* d_slots,
+                                  uint64_t stride, uint32_t* d_sizes, uint32_t with_ext, void* stream)
+{
+    return encode_blocks_impl(c, d_in, total, block, d_slots, stride, d_sizes, nullptr, with_ext, stream);
+}
+
+extern "C" int tsqb_decode_blocks(tsqb_context* c, const uint8_t* d_comp, const uint64_t* d_offsets, uint64_t stride,
+                                  const uint32_t* d_comp_sizes, uint64_t nb, uint8_t* d_out, uint64_t out_stride,
+                                  uint32_t* d_out_sizes, uint32_t with_ext, void* stream)
+{
+    if (!c) return fail("tsqb_decode_blocks: null context");
+    if (nb == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    DecodeArgs a;
+    a.comp = d_comp; a.offs = d_offsets; a.stride = stride; a.csizes = d_comp_sizes; a.nb = nb;
+    a.out = d_out; a.ostride = out_stride; a.osizes = d_out_sizes;
+    CU(launch_decode(a, c->decode_lanes, with_ext != 0, c->sm_count, (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int tsqb_pack_container(tsqb_context* c, const uint8_t* d_slots, uint64_t stride, const uint32_t* d_sizes,
+                                   uint64_t nb, uint64_t total_u, uint32_t with_ext, uint8_t* d_container,
+                                   uint64_t* d_total_out, void* stream)
+{
+    if (!c) return fail("tsqb_pack_container: null context");
+    CU(cudaSetDevice(c->device));
+    if (c->offs.ensure((nb + 1) * sizeof(uint64_t))) return fail("tsqb_pack_container: out of device memory");
+    CU(launch_pack(d_slots, stride, d_sizes, nb, total_u, with_ext, d_container, d_total_out, (uint64_t*)c->offs.p,
+                   (cudaStream_t)stream));
+    return 0;
+}
+
+extern "C" int tsqb_index_container(tsqb_context* c, const uint8_t* d_container, uint64_t csize, uint64_t max_blocks,
+                                    uint64_t* d_offsets, uint32_t* d_sizes, uint32_t* d_ext, uint64_t* d_n, void* stream)
+{
+    if (!c) return fail("tsqb_index_container: null context");
+    CU(cudaSetDevice(c->device));
+    CU(launch_index(d_container, csize, max_blocks, d_offsets, d_sizes, d_ext, d_n, (cudaStream_t)stream));
+    return 0;
+}
+
+// --------------------------------------------------------------------------- host-buffer convenience
+// `tail` (optional, <= TSQB_INPUT_PAD bytes) are the bytes that follow the input in the caller's memory.
+static int stage_input(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n)
+{
+    if (c->in.ensure(total + 2 * TSQB_INPUT_PAD)) return fail("out of device memory for %llu input bytes", (unsigned long long)total);
+    uint8_t* d = (uint8_t*)c->in.p;
+    CU(cudaMemsetAsync(d + total, 0, 2 * TSQB_INPUT_PAD, c->stream));
+    CU(cudaMemcpyAsync(d, in, total, cudaMemcpyHostToDevice, c->stream));
+    if (tail && tail_n) CU(cudaMemcpyAsync(d + total, tail, tail_n, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+extern "C" int tsqb_encode_host(tsqb_context* c, const uint8_t* in, uint64_t total, uint32_t block, uint8_t* slots,
+                                uint32_t* sizes, uint32_t with_ext)
+{
+    if (!c) return fail("tsqb_encode_host: null context");
+    if (block == 0 || block > kBlockMax) return fail("tsqb_encode_host: bad block size %u", block);
+    if (total == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
+    if (stage_input(c, in, total, nullptr, 0)) return 1;
+    if (c->slots.ensure(nb * stride) || c->sizes.ensure(nb * 4)) return fail("tsqb_encode_host: out of device memory");
+    if (tsqb_encode_blocks(c, (uint8_t*)c->in.p, total, block, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, with_ext, c->stream)) return 1;
+    CU(cudaMemcpyAsync(sizes, c->sizes.p, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // only the used bytes of every slot travel back
+    for (uint64_t b = 0; b < nb; b++)
+        CU(cudaMemcpyAsync(slots + b * stride, (uint8_t*)c->slots.p + b * stride, sizes[b], cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int tsqb_decode_host(tsqb_context* c, const uint8_t* slots, uint64_t stride, const uint32_t* comp_sizes, uint64_t nb,
+                                uint8_t* out, uint64_t out_stride, uint32_t* out_sizes, uint32_t with_ext)
+{
+    if (!c) return fail("tsqb_decode_host: null context");
+    if (nb == 0) return 0;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    if (c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4) || c->out.ensure(nb * out_stride) || c->osizes.ensure(nb * 4))
+        return fail("tsqb_decode_host: out of device memory");
+    if (comp_sizes) {
+        for (uint64_t b = 0; b < nb; b++)
+            CU(cudaMemcpyAsync((uint8_t*)c->slots.p + b * stride, slots + b * stride, comp_sizes[b] < stride ? comp_sizes[b] : stride,
+                               cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(c->sizes.p, comp_sizes, nb * 4, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CU(cudaMemcpyAsync(c->slots.p, slots, nb * stride, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (tsqb_decode_blocks(c, (uint8_t*)c->slots.p, nullptr, stride, comp_sizes ? (uint32_t*)c->sizes.p : nullptr, nb,
+                           (uint8_t*)c->out.p, out_stride, (uint32_t*)c->osizes.p, with_ext, c->stream)) return 1;
+    CU(cudaMemcpyAsync(out_sizes, c->osizes.p, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // contiguous output: one copy when blocks are packed back to back
+    CU(cudaMemcpyAsync(out, c->out.p, (nb - 1) * out_stride + out_sizes[nb - 1], cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+// `tail`: see stage_input.  Container is assembled on the device and comes back in one copy.
+static int compress_buffer_locked(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n,
+                                  uint32_t block, uint32_t with_ext, uint8_t** out, uint64_t* out_size)
+{
+    const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
+    if (stage_input(c, in, total, tail, tail_n)) return 1;
+    const uint64_t cap = 16 + nb * (stride + 3);
+    if (c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) || c->cont.ensure(cap + 256) || c->misc.ensure(64))
+        return fail("compress: out of device memory");
+    if (nb && tsqb_encode_blocks(c, (uint8_t*)c->in.p, total, block, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, with_ext, c->stream)) return 1;
+    if (tsqb_pack_container(c, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, nb, total, with_ext, (uint8_t*)c->cont.p,
+                            (uint64_t*)c->misc.p, c->stream)) return 1;
+    uint64_t clen = 0;
+    CU(cudaMemcpyAsync(&clen, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint8_t* host = (uint8_t*)malloc(clen ? clen : 1);
+    if (!host) return fail("compress: malloc(%llu) failed", (unsigned long long)clen);
+    CU(cudaMemcpyAsync(host, c->cont.p, clen, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = host; *out_size = clen;
+    return 0;
+}
+
+extern "C" int tsqb_compress_buffer(tsqb_context* c, const uint8_t* in, uint64_t total, uint32_t block, uint32_t with_ext,
+                                    uint8_t** out, uint64_t* out_size)
+{
+    if (!c || !out || !out_size) return fail("tsqb_compress_buffer: null argument");
+    if (block == 0 || block > kBlockMax) return fail("tsqb_compress_buffer: bad block size %u", block);
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    return compress_buffer_locked(c, in, total, nullptr, 0, block, with_ext, out, out_size);
+}
+
+extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t** out, uint64_t* out_size)
+{
+    if (!c || !in || !out || !out_size) return fail("tsqb_decompress_buffer: null argument");
+    if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_buffer: not a TSQ1 container");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    uint32_t nb_hdr; uint64_t total_hdr;
+    memcpy(&nb_hdr, in + 4, 4); memcpy(&total_hdr, in + 8, 8);
+    // the header's counts are not trusted beyond sizing (turbosqueeze.cpp:110-117 ignores them)
+    const uint64_t max_blocks = (in_size - 16) / 4 + 1 < (uint64_t)nb_hdr + 1 ? (in_size - 16) / 4 + 1 : (uint64_t)nb_hdr + 1;
+    if (c->cont.ensure(in_size + 512) || c->offs.ensure(max_blocks * 8) || c->sizes.ensure(max_blocks * 4) || c->ext.ensure(max_blocks * 4) ||
+        c->osizes.ensure(max_blocks * 4) || c->misc.ensure(64))
+        return fail("decompress: out of device memory");
+    CU(cudaMemcpyAsync(c->cont.p, in, in_size, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync((uint8_t*)c->cont.p + in_size, 0, 512, c->stream));
+    if (tsqb_index_container(c, (uint8_t*)c->cont.p, in_size, max_blocks, (uint64_t*)c->offs.p, (uint32_t*)c->sizes.p,
+                             (uint32_t*)c->ext.p, (uint64_t*)c->misc.p, c->stream)) return 1;
+    uint64_t nb = 0;
+    CU(cudaMemcpyAsync(&nb, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // every block but the last must be a full block of the same size: read the first header to get it
+    uint32_t with_ext = 0, block = 0;
+    std::vector<uint64_t> offs(nb);
+    std::vector<uint32_t> exts(nb);
+    if (nb) {
+        CU(cudaMemcpy(offs.data(), c->offs.p, nb * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(exts.data(), c->ext.p, nb * 4, cudaMemcpyDeviceToHost));
+        with_ext = exts[0];
+        for (uint64_t b = 0; b < nb; b++) {
+            if (exts[b] != with_ext) return fail("decompress: mixed extension flags in one container are not supported on the device path");
+            const uint8_t* h = in + offs[b];
+            const uint32_t u = (uint32_t)h[0] | ((uint32_t)h[1] << 8) | ((uint32_t)h[2] << 16);
+            if (u > kBlockMax) return fail("decompress: block %llu declares %u bytes (> 4 MiB)", (unsigned long long)b, u);
+            if (b == 0) block = u;
+            else if (b + 1 < nb ? u != block : u > block) { block = 0; break; }
+        }
+        if (block == 0) block = kBlockMax;      // irregular container: one 4 MiB stride per block, compacted on the host
+    }
+    const uint64_t ostride = block;
+    if (nb && c->out.ensure(nb * ostride)) return fail("decompress: out of device memory");
+    if (nb && tsqb_decode_blocks(c, (uint8_t*)c->cont.p, (uint64_t*)c->offs.p, 0, (uint32_t*)c->sizes.p, nb, (uint8_t*)c->out.p, ostride,
+                                 (uint32_t*)c->osizes.p, with_ext, c->stream)) return 1;
+    std::vector<uint32_t> osz(nb);
+    if (nb) CU(cudaMemcpyAsync(osz.data(), c->osizes.p, nb * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint64_t total = 0;
+    bool packed = true;
+    for (uint64_t b = 0; b < nb; b++) { if (b + 1 < nb && osz[b] != ostride) packed = false; total += osz[b]; }
+    uint8_t* host = (uint8_t*)malloc(total + 128);                 // tsq_threads.cpp:795 allocates outsize+128
+    if (!host) return fail("decompress: malloc failed");
+    if (packed) {
+        if (total) CU(cudaMemcpyAsync(host, c->out.p, total, cudaMemcpyDeviceToHost, c->stream));
+    } else {
+        uint64_t at = 0;
+        for (uint64_t b = 0; b < nb; b++) {
+            if (osz[b]) CU(cudaMemcpyAsync(host + at, (uint8_t*)c->out.p + b * ostride, osz[b], cudaMemcpyDeviceToHost, c->stream));
+            at += osz[b];
+        }
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    *out = host; *out_size = total;
+    (void)total_hdr;
+    return 0;
+}
+
+// ------------------------------------------------------------- layer 2: the reference's entry points
+static tsqb_context* g_default = nullptr;
+static std::mutex g_default_mtx;
+
+static tsqb_context* default_context()
+{
+    std::lock_guard<std::mutex> lk(g_default_mtx);
+    if (!g_default && tsqb_create(&g_default, 0) != 0) {
+        fprintf(stderr, "turbosqueeze_b200: %s\n", tsqb_last_error());
+        g_default = nullptr;
+    }
+    return g_default;
+}
+
+// tsq_context.cpp:56-74 -- the table is kept (128-byte aligned, 256 KiB) because callers poke it
+// (test/test.cpp:42); the device path defines the table as zero at entry and never reads this copy.
+extern "C" struct TSQCompressionContext* tsqAllocateContext(void)
+{
+    TSQCompressionContext* ctx = (TSQCompressionContext*)malloc(sizeof(TSQCompressionContext));
+    if (!ctx) return nullptr;
+    ctx->refhash = (uint16_t*)aligned_alloc(128, TSQB_HASH_BYTES);
+    if (!ctx->refhash) { free(ctx); return nullptr; }
+    return ctx;
+}
+
+extern "C" void tsqDeallocateContext(struct TSQCompressionContext* ctx)
+{
+    if (!ctx) return;
+    free(ctx->refhash);
+    free(ctx);
+}
+
+extern "C" void tsqInit(struct TSQCompressionContext* ctx)          // tsq_context.cpp:77-80
+{
+    if (ctx && ctx->refhash) memset(ctx->refhash, 0, TSQB_HASH_BYTES);
+}
+
+extern "C" void tsqEncode(struct TSQCompressionContext* ctx, uint8_t* in, uint8_t* out, uint32_t* outputSize, uint32_t inputSize,
+                          uint32_t withExtensions)
+{
+    (void)ctx;
+    if (outputSize) *outputSize = 0;
+    tsqb_context* c = default_context();
+    if (!c || !in || !out || !outputSize || inputSize == 0 || inputSize > kBlockMax) return;
+    std::lock_guard<std::mutex> lk(c->mtx);
+    const uint64_t stride = tsqb_slot_stride(inputSize);
+    // the reference reads <= 19 bytes past the block (72 with extensions): ship exactly those
+    const uint32_t tail_n = withExtensions ? 72u : 19u;
+    if (cudaSetDevice(c->device) != cudaSuccess || stage_input(c, in, inputSize, in + inputSize, tail_n)) goto bad;
+    if (c->slots.ensure(stride) || c->sizes.ensure(8)) goto bad;
+    if (encode_blocks_impl(c, (uint8_t*)c->in.p, inputSize, inputSize, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p,
+                           (uint32_t*)c->sizes.p + 1, withExtensions, c->stream)) goto bad;
+    {
+        uint32_t nf[2] = {0, 0};                                     // size, kTail* flags
+        if (cudaMemcpyAsync(nf, c->sizes.p, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) goto bad;
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) goto bad;
+        const uint32_t n = nf[0];
+        // The last two bytes may be ones the reference never initialises (tsq_encode.cpp:176-188):
+        // there the caller's own pre-fill of `outputBlock` must survive, exactly as in the reference.
+        uint8_t tail[2] = {0, 0};
+        const uint32_t body = n >= 2 ? n - 2 : 0;
+        if (body && cudaMemcpy(out, c->slots.p, body, cudaMemcpyDeviceToHost) != cudaSuccess) goto bad;
+        if (cudaMemcpy(tail, (uint8_t*)c->slots.p + body, n - body, cudaMemcpyDeviceToHost) != cudaSuccess) goto bad;
+        if (n >= 2) {
+            if (!(nf[1] & 1u)) out[n - 2] = tail[0];
+            if (nf[1] & 4u) out[n - 1] = (uint8_t)(out[n - 1] << 4);
+            else if (!(nf[1] & 2u)) out[n - 1] = tail[1];
+        } else if (n == 1) out[0] = tail[0];
+        *outputSize = n;
+    }
+    return;
+bad:
+    cudaGetLastError();
+    fprintf(stderr, "turbosqueeze_b200: tsqEncode failed: %s\n", tsqb_last_error());
+}
+
+extern "C" void tsqDecode(uint8_t* in, uint8_t* out, uint32_t* outputSize, uint32_t inputSize, uint32_t withExtensions)
+{
+    if (outputSize) *outputSize = 0;
+    tsqb_context* c = default_context();
+    if (!c || !in || !out || !outputSize) return;
+    const uint32_t size = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16);
+    if (size > kBlockMax) return;                                    // tsq_decode.cpp:53
+    std::lock_guard<std::mutex> lk(c->mtx);
+    // the reference ignores inputSize (tsq_decode.cpp:42-126); without it the worst case is shipped
+    uint64_t n_in = inputSize ? inputSize : tsqb_slot_stride(size);
+    if (cudaSetDevice(c->device) != cudaSuccess) goto bad;
+    if (c->slots.ensure(n_in + 512) || c->sizes.ensure(4) || c->out.ensure((uint64_t)size + 16) || c->osizes.ensure(4)) goto bad;
+    if (cudaMemsetAsync((uint8_t*)c->slots.p + n_in, 0, 512, c->stream) != cudaSuccess) goto bad;
+    if (cudaMemcpyAsync(c->slots.p, in, n_in, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) goto bad;
+    {
+        const uint32_t lim = (uint32_t)(n_in + 256);
+        if (cudaMemcpyAsync(c->sizes.p, &lim, 4, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) goto bad;
+    }
+    if (tsqb_decode_blocks(c, (uint8_t*)c->slots.p, nullptr, 0, (uint32_t*)c->sizes.p, 1, (uint8_t*)c->out.p, size ? size : 1,
+                           (uint32_t*)c->osizes.p, withExtensions, c->stream)) goto bad;
+    if (size && cudaMemcpyAsync(out, c->out.p, size, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) goto bad;
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) goto bad;
+    *outputSize = size;                                              // tsq_decode.cpp:125
+    return;
+bad:
+    cudaGetLastError();
+    fprintf(stderr, "turbosqueeze_b200: tsqDecode failed: %s\n", tsqb_last_error());
+}
+
+static bool read_all(FILE* f, std::vector<uint8_t>& v)
+{
+    if (fseek(f, 0, SEEK_END) == 0) {                                // turbosqueeze.cpp:57-59
+        const long n = ftell(f);
+        if (n < 0 || fseek(f, 0, SEEK_SET) != 0) return false;
+        v.resize((size_t)n);
+        return n == 0 || fread(v.data(), 1, (size_t)n, f) == (size_t)n;
+    }
+    uint8_t buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) v.insert(v.end(), buf, buf + n);
+    return true;
+}
+
+extern "C" void tsqCompress(FILE* in, FILE* out, bool useextensions, uint32_t level)
+{
+    (void)level;                                                     // never read by the reference either
+    tsqb_context* c = default_context();
+    if (!c || !in || !out) return;
+    std::vector<uint8_t> data;
+    if (!read_all(in, data)) return;
+    uint8_t* blob = nullptr; uint64_t n = 0;
+    if (tsqb_compress_buffer(c, data.data(), data.size(), kBlockMax, useextensions ? 1u : 0u, &blob, &n) != 0) {
+        fprintf(stderr, "turbosqueeze_b200: tsqCompress failed: %s\n", tsqb_last_error());
+        return;
+    }
+    fwrite(blob, 1, n, out);
+    free(blob);
+}
+
+extern "C" void tsqDecompress(FILE* in, FILE* out)
+{
+    tsqb_context* c = default_context();
+    if (!c || !in || !out) return;
+    std::vector<uint8_t> data;
+    if (!read_all(in, data)) return;
+    if (data.size() < 16 || memcmp(data.data(), "TSQ1", 4) != 0) return;   // turbosqueeze.cpp:107-109
+    uint8_t* blob = nullptr; uint64_t n = 0;
+    if (tsqb_decompress_buffer(c, data.data(), data.size(), &blob, &n) != 0) {
+        fprintf(stderr, "turbosqueeze_b200: tsqDecompress failed: %s\n", tsqb_last_error());
+        return;
+    }
+    fwrite(blob, 1, n, out);
+    free(blob);
+}
+
+// ---- synchronous buffer API (tsq_threads.cpp:413-441, :862-890)
+struct TSQCompressionContext_MT   { tsqb_context* dev; bool verbose; };
+struct TSQDecompressionContext_MT { tsqb_context* dev; bool verbose; };
+
+extern "C" struct TSQCompressionContext_MT* tsqAllocateContextCompression_MT(bool verbose)
+{
+    tsqb_context* d = nullptr;
+    if (tsqb_create(&d, 0) != 0) { if (verbose) printf("Error: %s\n", tsqb_last_error()); return nullptr; }
+    return new TSQCompressionContext_MT{d, verbose};
+}
+
+extern "C" void tsqDeallocateContextCompression_MT(struct TSQCompressionContext_MT* ctx)
+{
+    if (!ctx) return;
+    tsqb_destroy(ctx->dev);
+    delete ctx;
+}
+
+extern "C" struct TSQDecompressionContext_MT* tsqAllocateContextDecompression_MT(bool verbose)
+{
+    tsqb_context* d = nullptr;
+    if (tsqb_create(&d, 0) != 0) { if (verbose) printf("Error: %s\n", tsqb_last_error()); return nullptr; }
+    return new TSQDecompressionContext_MT{d, verbose};
+}
+
+extern "C" void tsqDeallocateContextDecompression_MT(struct TSQDecompressionContext_MT* ctx)
+{
+    if (!ctx) return;
+    tsqb_destroy(ctx->dev);
+    delete ctx;
+}
+
+static bool load_input(uint8_t* in, size_t szin, bool infile, std::vector<uint8_t>& store, const uint8_t** p, size_t* n, bool verbose)
+{
+    if (!infile) { *p = in; *n = szin; return true; }
+    FILE* f = fopen((const char*)in, "rb");                          // tsq_threads.cpp:294
+    if (!f) { if (verbose) printf("Error: could not open input file.\n"); return false; }
+    const bool ok = read_all(f, store);
+    fclose(f);
+    *p = store.data(); *n = store.size();
+    return ok;
+}
+
+static bool store_output(uint8_t* blob, uint64_t n, uint8_t** out, size_t* szout, bool outfile, bool verbose)
+{
+    if (!outfile) { *out = blob; *szout = (size_t)n; return true; }
+    FILE* f = fopen((const char*)*out, "wb");                        // tsq_threads.cpp:319
+    bool ok = f != nullptr;
+    if (!f && verbose) printf("Error: could not open output file.\n");
+    if (f) { ok = fwrite(blob, 1, n, f) == n; fclose(f); }
+    free(blob);
+    if (ok && szout) *szout = (size_t)n;
+    return ok;
+}
+
+extern "C" bool tsqCompress_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
+                               bool outfile, bool useextensions, uint32_t level)
+{
+    (void)level;
+    if (!ctx || !in || szin == 0 || !out || szout == 0) return false;          // tsq_threads.cpp:415-418
+    std::vector<uint8_t> store;
+    const uint8_t* p; size_t n;
+    if (!load_input(in, szin, infile, store, &p, &n, ctx->verbose)) return false;
+    uint8_t* blob = nullptr; uint64_t bn = 0;
+    if (tsqb_compress_buffer(ctx->dev, p, n, kBlockMax, useextensions ? 1u : 0u, &blob, &bn) != 0) {
+        if (ctx->verbose) printf("Error: %s\n", tsqb_last_error());
+        return false;
+    }
+    return store_output(blob, bn, out, szout, outfile, ctx->verbose);
+}
+
+extern "C" bool tsqDecompress_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
+                                 bool outfile)
+{
+    if (!ctx || !in || szin == 0 || !out || szout == 0) return false;          // tsq_threads.cpp:864-867
+    std::vector<uint8_t> store;
+    const uint8_t* p; size_t n;
+    if (!load_input(in, szin, infile, store, &p, &n, ctx->verbose)) return false;
+    uint8_t* blob = nullptr; uint64_t bn = 0;
+    if (tsqb_decompress_buffer(ctx->dev, p, n, &blob, &bn) != 0) {
+        if (ctx->verbose) printf("Error: %s\n", tsqb_last_error());
+        return false;
+    }
+    return store_output(blob, bn, out, szout, outfile, ctx->verbose);
+}

@@ -1,0 +1,52 @@
+// tsq_device.cuh -- launch interface between the C-ABI (tsq_capi.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tsqb {
+
+constexpr uint32_t kBlockMax   = 1u << 22;          // TSQ_BLOCK_SZ   (reference turbosqueeze.h:38)
+constexpr uint32_t kHashSlots  = 1u << 17;          // 2^TSQ_HASH_BITS (reference turbosqueeze.h:41)
+constexpr uint32_t kHashMask   = kHashSlots - 1u;
+constexpr uint32_t kTableBytes = kHashSlots * 2u;   // TSQ_HASH_SZ
+
+struct EncodeArgs {
+    const uint8_t* in;        // contiguous input, `total` bytes + >= 128 readable
+    uint64_t       total;
+    uint32_t       block;     // block size
+    uint64_t       nb;        // number of blocks
+    uint8_t*       slots;     // block b -> slots + b * stride
+    uint64_t       stride;
+    uint32_t*      sizes;     // compressed size per block
+    uint32_t*      tailflags; // optional: kTail* flags per block (see tsq_encode_common.cuh)
+    uint16_t*      tables;    // n_slots tables of kHashSlots u16
+    uint32_t       n_slots;
+};
+
+struct DecodeArgs {
+    const uint8_t*  comp;
+    const uint64_t* offs;     // optional explicit stream offsets
+    uint64_t        stride;
+    const uint32_t* csizes;   // optional readable bytes per stream
+    uint64_t        nb;
+    uint8_t*        out;      // block b -> out + b * ostride
+    uint64_t        ostride;
+    uint32_t*       osizes;
+};
+
+// encode_impl: 1 = scalar (one thread per block), 2 = warp per block.
+cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int sm_count, cudaStream_t st);
+// how many hash tables launch_encode(impl) will use for nb blocks (caller sizes a.tables from it)
+uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);
+
+// lanes: lanes cooperating on one block (1..32, power of two)
+cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st);
+int         decode_lanes_auto(uint64_t nb, int sm_count);
+
+cudaError_t launch_pack(const uint8_t* slots, uint64_t stride, const uint32_t* sizes, uint64_t nb,
+                        uint64_t total_u, uint32_t ext, uint8_t* container, uint64_t* total_out,
+                        uint64_t* scratch_offsets, cudaStream_t st);
+cudaError_t launch_index(const uint8_t* container, uint64_t csize, uint64_t max_blocks, uint64_t* offs,
+                         uint32_t* sizes, uint32_t* ext_flags, uint64_t* n_blocks, cudaStream_t st);
+
+}  // namespace tsqb
