@@ -58,6 +58,9 @@ typedef struct tsqb_context tsqb_context;          /* opaque: device ordinal + h
 /* Last error of the calling thread ("" when none). */
 const char* tsqb_last_error(void);
 
+/* Kernels launched by this library so far in this process (bench.py's gpu_launches). */
+uint64_t tsqb_launch_count(void);
+
 /* Number of usable CUDA devices (0 when there is none; never falls back to the CPU). */
 int tsqb_device_count(void);
 
@@ -141,6 +144,11 @@ int tsqb_compress_buffer(tsqb_context* ctx, const uint8_t* in, uint64_t total, u
                          uint32_t with_ext, uint8_t** out, uint64_t* out_size);
 int tsqb_decompress_buffer(tsqb_context* ctx, const uint8_t* in, uint64_t in_size, uint8_t** out,
                            uint64_t* out_size);
+/* Same, into a caller-owned host buffer (pinned memory makes both PCIe legs run at link speed). */
+int tsqb_compress_into(tsqb_context* ctx, const uint8_t* in, uint64_t total, uint32_t block_size,
+                       uint32_t with_ext, uint8_t* out, uint64_t out_capacity, uint64_t* out_size);
+int tsqb_decompress_into(tsqb_context* ctx, const uint8_t* in, uint64_t in_size, uint8_t* out,
+                         uint64_t out_capacity, uint64_t* out_size);
 
 /* ------------------------------------------------------------------------------------------------
  * Layer 2: the reference's entry points (reference turbosqueeze.h, line cited on each)

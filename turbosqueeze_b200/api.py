@@ -40,6 +40,7 @@ def library():
     L = C.CDLL(path)
     L.tsqb_last_error.restype = C.c_char_p
     L.tsqb_device_count.restype = C.c_int
+    L.tsqb_launch_count.restype = C.c_uint64
     L.tsqb_create.argtypes = [C.POINTER(_vp), C.c_int]
     L.tsqb_destroy.argtypes = [_vp]
     L.tsqb_destroy.restype = None
@@ -54,6 +55,8 @@ def library():
     L.tsqb_decode_host.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.c_uint64, _vp, C.c_uint32]
     L.tsqb_compress_buffer.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(_vp), C.POINTER(C.c_uint64)]
     L.tsqb_decompress_buffer.argtypes = [_vp, _vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint64)]
+    L.tsqb_compress_into.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.tsqb_decompress_into.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.tsqAllocateContext.restype = _vp
     L.tsqDeallocateContext.argtypes = [_vp]
     L.tsqDeallocateContext.restype = None
@@ -209,6 +212,17 @@ class Context:
             return C.string_at(out, n.value)
         finally:
             _libc.free(out)
+
+    def compress_into(self, in_ptr, total, block, ext, out_ptr, out_cap):
+        """Host pointer -> TSQ1 container in a caller-owned host buffer; returns its length."""
+        n = C.c_uint64(0)
+        _check(library().tsqb_compress_into(self._h, in_ptr, total, block, int(ext), out_ptr, out_cap, C.byref(n)), "tsqb_compress_into")
+        return n.value
+
+    def decompress_into(self, in_ptr, in_size, out_ptr, out_cap):
+        n = C.c_uint64(0)
+        _check(library().tsqb_decompress_into(self._h, in_ptr, in_size, out_ptr, out_cap, C.byref(n)), "tsqb_decompress_into")
+        return n.value
 
     def decompress_buffer(self, blob):
         a = _as_np(blob)

@@ -7,6 +7,7 @@
 #include "../../include/tsq_b200.h"
 #include "tsq_device.cuh"
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -37,6 +38,9 @@ static int fail(const char* fmt, ...)
     } while (0)
 
 extern "C" const char* tsqb_last_error(void) { return g_err.c_str(); }
+
+static std::atomic<uint64_t> g_launches{0};
+extern "C" uint64_t tsqb_launch_count(void) { return g_launches.load(); }
 
 extern "C" int tsqb_device_count(void)
 {
@@ -141,6 +145,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     if (c->tables.ensure((size_t)a.n_slots * kTableBytes)) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
     a.tables = (uint16_t*)c->tables.p;
     CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
+    g_launches += 1;
     return 0;
 }
 
@@ -161,6 +166,7 @@ extern "C" int tsqb_decode_blocks(tsqb_context* c, const uint8_t* d_comp, const 
     a.comp = d_comp; a.offs = d_offsets; a.stride = stride; a.csizes = d_comp_sizes; a.nb = nb;
     a.out = d_out; a.ostride = out_stride; a.osizes = d_out_sizes;
     CU(launch_decode(a, c->decode_lanes, with_ext != 0, c->sm_count, (cudaStream_t)stream));
+    g_launches += 1;
     return 0;
 }
 
@@ -173,6 +179,7 @@ extern "C" int tsqb_pack_container(tsqb_context* c, const uint8_t* d_slots, uint
     if (c->offs.ensure((nb + 1) * sizeof(uint64_t))) return fail("tsqb_pack_container: out of device memory");
     CU(launch_pack(d_slots, stride, d_sizes, nb, total_u, with_ext, d_container, d_total_out, (uint64_t*)c->offs.p,
                    (cudaStream_t)stream));
+    g_launches += nb ? 2 : 1;
     return 0;
 }
 
@@ -182,6 +189,7 @@ extern "C" int tsqb_index_container(tsqb_context* c, const uint8_t* d_container,
     if (!c) return fail("tsqb_index_container: null context");
     CU(cudaSetDevice(c->device));
     CU(launch_index(d_container, csize, max_blocks, d_offsets, d_sizes, d_ext, d_n, (cudaStream_t)stream));
+    g_launches += 1;
     return 0;
 }
 
@@ -245,9 +253,10 @@ extern "C" int tsqb_decode_host(tsqb_context* c, const uint8_t* slots, uint64_t 
     return 0;
 }
 
-// `tail`: see stage_input.  Container is assembled on the device and comes back in one copy.
-static int compress_buffer_locked(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n,
-                                  uint32_t block, uint32_t with_ext, uint8_t** out, uint64_t* out_size)
+// `tail`: see stage_input.  Container is assembled on the device and comes back in one copy, either
+// into a fresh malloc (host_out == nullptr) or into the caller's buffer of `host_cap` bytes.
+static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
+                           uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size)
 {
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
     if (stage_input(c, in, total, tail, tail_n)) return 1;
@@ -260,11 +269,17 @@ static int compress_buffer_locked(tsqb_context* c, const uint8_t* in, uint64_t t
     uint64_t clen = 0;
     CU(cudaMemcpyAsync(&clen, c->misc.p, 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    uint8_t* host = (uint8_t*)malloc(clen ? clen : 1);
-    if (!host) return fail("compress: malloc(%llu) failed", (unsigned long long)clen);
+    uint8_t* host = host_out;
+    if (!host) {
+        host = (uint8_t*)malloc(clen ? clen : 1);
+        if (!host) return fail("compress: malloc(%llu) failed", (unsigned long long)clen);
+    } else if (clen > host_cap) {
+        return fail("compress: output needs %llu bytes, caller gave %llu", (unsigned long long)clen, (unsigned long long)host_cap);
+    }
     CU(cudaMemcpyAsync(host, c->cont.p, clen, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    *out = host; *out_size = clen;
+    if (out) *out = host;
+    *out_size = clen;
     return 0;
 }
 
@@ -275,15 +290,22 @@ extern "C" int tsqb_compress_buffer(tsqb_context* c, const uint8_t* in, uint64_t
     if (block == 0 || block > kBlockMax) return fail("tsqb_compress_buffer: bad block size %u", block);
     std::lock_guard<std::mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
-    return compress_buffer_locked(c, in, total, nullptr, 0, block, with_ext, out, out_size);
+    return compress_locked(c, in, total, nullptr, 0, block, with_ext, nullptr, 0, out, out_size);
 }
 
-extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t** out, uint64_t* out_size)
+extern "C" int tsqb_compress_into(tsqb_context* c, const uint8_t* in, uint64_t total, uint32_t block, uint32_t with_ext,
+                                  uint8_t* out, uint64_t out_capacity, uint64_t* out_size)
 {
-    if (!c || !in || !out || !out_size) return fail("tsqb_decompress_buffer: null argument");
-    if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_buffer: not a TSQ1 container");
+    if (!c || !out || !out_size) return fail("tsqb_compress_into: null argument");
+    if (block == 0 || block > kBlockMax) return fail("tsqb_compress_into: bad block size %u", block);
     std::lock_guard<std::mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
+    return compress_locked(c, in, total, nullptr, 0, block, with_ext, out, out_capacity, nullptr, out_size);
+}
+
+static int decompress_locked(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* host_out, uint64_t host_cap,
+                             uint8_t** out, uint64_t* out_size)
+{
     uint32_t nb_hdr; uint64_t total_hdr;
     memcpy(&nb_hdr, in + 4, 4); memcpy(&total_hdr, in + 8, 8);
     // the header's counts are not trusted beyond sizing (turbosqueeze.cpp:110-117 ignores them)
@@ -326,8 +348,13 @@ extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64
     uint64_t total = 0;
     bool packed = true;
     for (uint64_t b = 0; b < nb; b++) { if (b + 1 < nb && osz[b] != ostride) packed = false; total += osz[b]; }
-    uint8_t* host = (uint8_t*)malloc(total + 128);                 // tsq_threads.cpp:795 allocates outsize+128
-    if (!host) return fail("decompress: malloc failed");
+    uint8_t* host = host_out;
+    if (!host) {
+        host = (uint8_t*)malloc(total + 128);                      // tsq_threads.cpp:795 allocates outsize+128
+        if (!host) return fail("decompress: malloc failed");
+    } else if (total > host_cap) {
+        return fail("decompress: output needs %llu bytes, caller gave %llu", (unsigned long long)total, (unsigned long long)host_cap);
+    }
     if (packed) {
         if (total) CU(cudaMemcpyAsync(host, c->out.p, total, cudaMemcpyDeviceToHost, c->stream));
     } else {
@@ -338,9 +365,29 @@ extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64
         }
     }
     CU(cudaStreamSynchronize(c->stream));
-    *out = host; *out_size = total;
+    if (out) *out = host;
+    *out_size = total;
     (void)total_hdr;
     return 0;
+}
+
+extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t** out, uint64_t* out_size)
+{
+    if (!c || !in || !out || !out_size) return fail("tsqb_decompress_buffer: null argument");
+    if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_buffer: not a TSQ1 container");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    return decompress_locked(c, in, in_size, nullptr, 0, out, out_size);
+}
+
+extern "C" int tsqb_decompress_into(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_capacity,
+                                    uint64_t* out_size)
+{
+    if (!c || !in || !out || !out_size) return fail("tsqb_decompress_into: null argument");
+    if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_into: not a TSQ1 container");
+    std::lock_guard<std::mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    return decompress_locked(c, in, in_size, out, out_capacity, nullptr, out_size);
 }
 
 // ------------------------------------------------------------- layer 2: the reference's entry points

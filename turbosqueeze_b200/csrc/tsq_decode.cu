@@ -138,9 +138,17 @@ static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
+cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
+
+// lanes: 0 = auto; 1..32 = sub-warp kernel with that many lanes per block; 33 = force the warp-per-block
+// step kernel (tsq_decode_warp.cu), 32 = force the pair-step kernel at full warp width
 cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st)
 {
-    if (lanes <= 0) lanes = decode_lanes_auto(a.nb, sm_count);
+    if (lanes <= 0) {
+        lanes = decode_lanes_auto(a.nb, sm_count);
+        if (lanes == 32 && !ext) lanes = 33;
+    }
+    if (lanes == 33) return ext ? cudaErrorInvalidValue : launch_decode_warp(a, sm_count, st);
 #define TSQB_CASE(Wv) case Wv: return ext ? launch_decode_t<Wv, true>(a, sm_count, st) : launch_decode_t<Wv, false>(a, sm_count, st);
     switch (lanes) {
         TSQB_CASE(1) TSQB_CASE(2) TSQB_CASE(4) TSQB_CASE(8) TSQB_CASE(16) TSQB_CASE(32)
