@@ -101,7 +101,7 @@ def test_encode_matches_reference_golden_vectors(torch, ctx, impl, ext):
 
 
 CASES = [(1, 1), (2, 2), (5, 5), (31, 31), (32, 32), (33, 33), (34, 34), (63, 64), (100, 100), (4096, 4096), (65535, 65535),
-         (65536, 65536), (65537, 65537), (70000, 70000), (200000, 65536), (1 << 20, 4096), (1 << 20, 1000), (3 << 20, 262144),
+         (65536, 65536), (65537, 65537), (70000, 70000), (200000, 65536), (200001, 66667), (1 << 20, 4096), (1 << 20, 1000), (3 << 20, 262144),
          ((3 << 20) + 12345, 262144), ((4 << 20) + 1, 1 << 22), (600000, 131072 + 7)]
 
 
@@ -132,16 +132,17 @@ def make_input(kind, n, seed):
     return W.fill(kind, n, seed=seed)
 
 
-@pytest.mark.parametrize("lanes", [33, 32, 16, 8, 4, 2, 1])
+@pytest.mark.parametrize("lanes", [34, 33, 32, 16, 8, 4, 2, 1])
 @pytest.mark.parametrize("ext", [0, 1])
 def test_decode_restores_input(torch, ctx, oracle, lanes, ext):
-    """lanes 33 = warp-per-block step kernel (tsq_decode_warp.cu), 1..32 = sub-warp pair-step kernel."""
-    if lanes == 33 and ext:
+    """lanes 34 = walker + copier kernel (tsq_decode_split.cu, the default), 33 = warp-per-block step
+    kernel (tsq_decode_warp.cu), 1..32 = sub-warp pair-step kernel."""
+    if lanes >= 33 and ext:
         pytest.skip("the step kernel is no-extension only; the extension format uses the pair-step kernel")
     ctx.set_option("decode_lanes", lanes)
     try:
         for kind in ("text", "random", "rep8", "zeros", "runs"):
-            for n, block in [(1, 1), (5, 5), (100, 100), (4096, 4096), (70000, 70000), (200000, 65536), (1 << 20, 4096),
+            for n, block in [(1, 1), (5, 5), (100, 100), (4096, 4096), (70000, 70000), (200000, 65536), (200001, 66667), (1 << 20, 4096),
                              ((3 << 20) + 12345, 262144), ((4 << 20) + 1, 1 << 22)]:
                 buf = make_input(kind, n, seed=n + 5)
                 slots, sizes, _ = oracle.encode_blocks(buf, n, block, ext)

@@ -124,6 +124,10 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
     if (!strcmp(key, "encode_impl"))  { c->encode_impl = (int)v; return 0; }
     if (!strcmp(key, "decode_lanes")) { c->decode_lanes = (int)v; return 0; }
     if (!strcmp(key, "encode_slots")) { c->encode_slots = v; return 0; }
+    if (!strcmp(key, "l2_fetch")) {                                  // 32 / 64 / 128: DRAM fetch granularity hint
+        cudaSetDevice(c->device);
+        return cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) == cudaSuccess ? 0 : 1;
+    }
     return 1;
 }
 

@@ -1,0 +1,531 @@
+// tsq_decode_split.cu -- the production no-extension decoder: one WALKER lane + one COPIER warp per block.
+//
+// Semantics: reference tsqDecodeNoext (tsq_decode.cpp:42-126), bit-exact on [0, size).
+//
+// Why two roles.  The token walk is a serial chain: the address of every size byte depends on the
+// payload lengths of the pair before it (tsq_decode.cpp:68-86), ~50 cycles per pair even from
+// shared memory, and it cannot be split inside a block.  Executed by a whole warp (as in
+// tsq_decode_warp.cu) that chain costs 32 lanes' worth of issue slots per instruction.  Here the
+// chains of up to 31 blocks are walked side by side by the lanes of ONE walker warp -- lane L walks
+// the stream of the CTA's block slot L -- so the serial part costs 1/31 of the issue slots, and it
+// runs ahead of the copy work instead of alternating with it.  The walker publishes one 8-byte
+// descriptor per pair (stream position of the size byte, output position, the pair's two control
+// bits) into a per-slot shared-memory queue.
+//
+// The copier warp of a slot consumes 16 descriptors (32 symbols) per step, one lane per symbol:
+//   * the compressed stream is staged into a shared-memory ring by 1-D bulk async copies
+//     (cp.async.bulk + mbarrier: TMA without a tensor map; SASS UBLKCP) issued by the copier;
+//   * decoded bytes go to a shared-memory OUTPUT ring first; near matches (distance < ring) read
+//     their source there (29-cycle LDS instead of an L2 round trip), far matches read HBM/L2 bytes
+//     that an earlier step flushed;
+//   * every symbol is stored as a blind 16-byte run in DESCENDING byte order: the garbage tail of
+//     symbol s lands on bytes owned by later symbols, and those write their own byte later in
+//     program order, so no per-byte predicate is needed (the reference uses the same blind copy,
+//     tsq_decode.cpp:74-85, serially);
+//   * symbols whose source lies inside the output of the same step wait for it in follow-up rounds
+//     (sources always precede their own pair, tsq_encode.cpp:139-141, so every round releases at
+//     least the first pending pair);
+//   * after the step, all complete 16-byte units of the output ring are written to HBM with
+//     coalesced 128-bit stores.  Nothing is ever written past the block's decoded size.
+#include "tsq_device.cuh"
+
+namespace tsqb {
+
+namespace {
+
+constexpr unsigned FULL      = 0xffffffffu;
+constexpr uint32_t kChunk    = 512;                  // bytes per bulk copy
+constexpr uint32_t kChunks   = 8;                    // ring slots
+constexpr uint32_t kInRing   = kChunk * kChunks;     // 4 KiB of stream per block slot
+constexpr uint32_t kInMask   = kInRing - 1;
+constexpr uint32_t kQueue    = 64;                   // descriptors per slot
+constexpr uint32_t kQMask    = kQueue - 1;
+constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
+constexpr uint32_t kLook     = 40;                   // stream bytes one pair can touch (1 + 1 + 16 + 16) + slack
+constexpr uint32_t kWalkers  = 4;                    // walker warps per CTA (one per warp scheduler), slots dealt round-robin
+constexpr uint32_t kMaxSlots = 32 - kWalkers;       // copier warps per CTA (copiers + walkers <= 1024 threads)
+
+constexpr uint32_t kDescEnd  = 0x80000000u;
+constexpr uint32_t kTagShift = 26;
+
+template <uint32_t OUT_RING>
+struct __align__(16) SlotSmem {
+    uint8_t  in_ring[kInRing];
+    uint8_t  out_ring[OUT_RING];
+    uint2    desc[kQueue];
+    uint64_t bar[kChunks];
+    // block hand-over copier -> walker (written before `ready`)
+    uint32_t ready;          // block index + 1 the slot is set up for
+    uint32_t phase_bits;     // mbarrier parities at block start
+    uint32_t limit_al;       // readable stream bytes, counted from the 16-byte aligned start
+    uint32_t nchunks;
+    uint32_t shift;          // stream start inside its first 16-byte unit
+    uint32_t consumed;       // copier -> walker: descriptors consumed so far (running count)
+    uint32_t produced;       // walker -> copier: descriptors published so far (running count)
+    uint32_t pad[1 + 12];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_vol_u32(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ uint2 ld_vol_u64(const uint2* p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_vol_u64(uint2* p, uint2 v)
+{
+    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y) : "memory");
+}
+
+// where block b's stream starts / how many bytes of it may be read
+__device__ __forceinline__ const uint8_t* stream_of(const DecodeArgs& a, uint64_t b, uint32_t& limit)
+{
+    limit = a.csizes ? a.csizes[b] : (a.stride > 0xffffffffull ? 0xffffffffu : (uint32_t)a.stride);
+    return a.comp + (a.offs ? a.offs[b] : b * a.stride);
+}
+
+// ------------------------------------------------------------------------------------------ walker
+// Lane L walks the token stream of slot L.  All lanes run the same loop; a lane that has to wait
+// (stream chunk not landed, descriptor queue full, copier still setting the block up) simply does
+// nothing in that iteration.
+template <uint32_t OUT_RING>
+__device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t nslots, uint32_t widx, unsigned lane)
+{
+    enum { P_DONE = 0, P_WAIT = 1, P_WALK = 2 };
+    const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
+    const uint32_t slot = lane * kWalkers + widx;             // walker warp widx owns slots widx, widx + kWalkers, ...
+    uint64_t b = (uint64_t)blockIdx.x * nslots + slot;
+    uint32_t phase = (slot < nslots && b < a.nb) ? P_WAIT : P_DONE;
+    SlotSmem<OUT_RING>& sm = slots[slot < nslots ? slot : 0];
+    const uint8_t* ring = sm.in_ring;
+
+    uint32_t p = 0, j = 0, size = 0, limit_al = 0, nchunks = 0, avail = 0, bits = 0;
+    uint32_t g = 0, ctl = 0;
+    uint32_t k = 0, cons = 0;                      // running descriptor counters (never reset)
+
+    // one pair: tsq_decode.cpp:68-86 without the copies.  CHECK = the block may end inside this pair.
+    auto pair_step = [&](uint32_t& pp, bool check) {
+        const uint32_t nib = ring[pp & kInMask];                                    // :68
+        const uint32_t tag = (k << (kTagShift - 6)) & (3u << kTagShift);            // ((k / kQueue) & 3) << kTagShift
+        st_vol_u64(&sm.desc[k & kQMask], make_uint2(pp | ((ctl & 0xC0u) << 18) | tag, j));
+        const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+        const uint32_t pay0 = (ctl & 0x80u) ? n0 + 1u : 2u;
+        const uint32_t pay1 = (ctl & 0x40u) ? n1 + 1u : 2u;
+        ctl <<= 2;
+        const uint32_t j1 = j + n0 + 1u;
+        const bool two = !check || j1 < size;                                       // second symbol exists
+        pp = pp + 1u + pay0 + (two ? pay1 : 0u);
+        j = j1 + (two ? n1 + 1u : 0u);
+        k++;
+    };
+
+    for (;;) {
+#pragma unroll 1
+        for (int rep = 0; rep < 8; rep++) {
+            if (phase == P_WALK) {
+                // take note of freshly landed chunks before deciding how far this lane may go
+                if (avail != nchunks && p + 4u * kLook > avail * kChunk) {
+                    const uint32_t s = avail % kChunks;
+                    if (mbar_test(&sm.bar[s], (bits >> s) & 1u)) { bits ^= 1u << s; avail++; }
+                }
+                // the 3-byte header needs the first chunk (tsq_decode.cpp:49-53)
+                if (size == 0xffffffffu) {
+                    if (avail >= 1u || avail == nchunks) {
+                        const uint32_t s0 = p;
+                        size = (uint32_t)ring[s0 & kInMask] | ((uint32_t)ring[(s0 + 1u) & kInMask] << 8) | ((uint32_t)ring[(s0 + 2u) & kInMask] << 16);
+                        if (!(size <= kBlockMax && size <= a.ostride) || nchunks == 0) size = 0;
+                        p = s0 + 3u;
+                    }
+                    continue;
+                }
+                const uint32_t have = (avail == nchunks) ? 0xffffffffu : avail * kChunk;
+                // a whole group (control byte + 4 full pairs) with no end-of-block inside it
+                const bool fast = (g & 3u) == 0 && p + 4u * kLook <= have && (k - cons) + 4u <= kQueue &&
+                                  j + 128u < size && p + 4u * kLook <= limit_al;
+                if (fast) {
+                    uint32_t pp = p + 1u;
+                    ctl = ring[p & kInMask];                                        // tsq_decode.cpp:62
+#pragma unroll
+                    for (int q = 0; q < 4; q++) pair_step(pp, false);
+                    p = pp;
+                    g += 4u;
+                    st_vol_u32(&sm.produced, k);
+                    continue;
+                }
+                const bool data_ok = p + kLook <= have;
+                const bool room    = (k - cons) < kQueue;
+                if (data_ok && room) {
+                    if (j < size && p < limit_al) {
+                        uint32_t pp = p;
+                        if ((g & 3u) == 0) { ctl = ring[pp & kInMask]; pp++; }
+                        pair_step(pp, true);
+                        p = pp;
+                        g++;
+                        st_vol_u32(&sm.produced, k);
+                    } else {
+                        const uint32_t tag = (k << (kTagShift - 6)) & (3u << kTagShift);
+                        st_vol_u64(&sm.desc[k & kQMask], make_uint2(kDescEnd | tag, j));
+                        k++;
+                        st_vol_u32(&sm.produced, k);
+                        b += stride_slots;
+                        phase = b < a.nb ? P_WAIT : P_DONE;
+                    }
+                } else {
+                    if (!room || (k - cons) + 4u > kQueue) cons = ld_vol_u32(&sm.consumed);
+                }
+            } else if (phase == P_WAIT) {
+                if (ld_vol_u32(&sm.ready) == (uint32_t)b + 1u) {
+                    __threadfence_block();
+                    bits     = ld_vol_u32(&sm.phase_bits);
+                    limit_al = ld_vol_u32(&sm.limit_al);
+                    nchunks  = ld_vol_u32(&sm.nchunks);
+                    p        = ld_vol_u32(&sm.shift);
+                    avail = 0; g = 0; ctl = 0; j = 0; size = 0xffffffffu;
+                    phase = P_WALK;
+                }
+            }
+        }
+        if (!__any_sync(FULL, phase != P_DONE)) break;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ copier
+// 16 bytes starting at byte `pos` of a power-of-two ring
+__device__ __forceinline__ void load16_ring(const uint8_t* ring, uint32_t mask, uint32_t pos, uint32_t v[4])
+{
+    const uint32_t a0 = pos & ~3u, sh = (pos & 3u) * 8u;
+    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(ring);
+    uint32_t w[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) w[m] = r32[((a0 + 4u * m) & mask) >> 2];
+#pragma unroll
+    for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
+}
+
+// blind 16-byte store, highest byte first (see the header comment).  `wrap` must be warp-uniform:
+// the ordering argument needs every participating lane to execute the same store sequence in lockstep.
+__device__ __forceinline__ void store16_desc(uint8_t* ring, uint32_t mask, uint32_t q, const uint32_t v[4], bool wrap)
+{
+    // volatile: the compiler must keep the stores in exactly this order
+    const uint32_t r = q & mask;
+    if (!wrap) {
+        volatile uint8_t* d = ring + r;
+#pragma unroll
+        for (int t = 15; t >= 0; t--) d[t] = (uint8_t)(v[t >> 2] >> (8 * (t & 3)));
+    } else {
+        volatile uint8_t* d = ring;
+#pragma unroll
+        for (int t = 15; t >= 0; t--) d[(q + (uint32_t)t) & mask] = (uint8_t)(v[t >> 2] >> (8 * (t & 3)));
+    }
+}
+
+// exact-length store (follow-up rounds: later symbols are already in place)
+__device__ __forceinline__ void store_exact(uint8_t* ring, uint32_t mask, uint32_t q, const uint32_t v[4], uint32_t len)
+{
+#pragma unroll
+    for (int t = 0; t < 16; t++)
+        if ((uint32_t)t < len) ring[(q + (uint32_t)t) & mask] = (uint8_t)(v[t >> 2] >> (8 * (t & 3)));
+}
+
+template <uint32_t OUT_RING>
+__device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slot, uint32_t nslots, unsigned lane)
+{
+    constexpr uint32_t kOMask = OUT_RING - 1;
+    const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
+    uint32_t phase = 0;                    // bit s: parity the next completion of ring slot s will have
+    uint32_t kc = 0;                       // running descriptor counter (mirrors the walker's k)
+    uint8_t* oring = sm.out_ring;
+    const uint8_t* iring = sm.in_ring;
+
+    for (uint64_t b = (uint64_t)blockIdx.x * nslots + slot; b < a.nb; b += stride_slots) {
+        uint32_t limit;
+        const uint8_t* src = stream_of(a, b, limit);
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint8_t* src_al = src - shift;
+        const uint32_t limit_al = shift + limit;
+        const uint32_t total_al = (limit_al + 15u) & ~15u;
+        const uint32_t nchunks = (total_al + kChunk - 1) / kChunk;
+        uint32_t issued = 0, waited = 0;
+
+        auto issue_upto = [&](uint32_t want) {                                   // all lanes call; lane 0 copies
+            want = min(want, nchunks);
+            if (lane == 0)
+                for (uint32_t n = issued; n < want; n++) {
+                    const uint32_t at = n * kChunk, bytes = min(kChunk, total_al - at);
+                    mbar_expect_tx(&sm.bar[n % kChunks], bytes);
+                    bulk_load(sm.in_ring + (at & kInMask), src_al + at, bytes, &sm.bar[n % kChunks]);
+                }
+            issued = max(issued, want);
+        };
+        auto wait_upto = [&](uint32_t want) {                                    // all lanes wait
+            want = min(want, issued);
+            for (; waited < want; waited++) {
+                const uint32_t s = waited % kChunks;
+                mbar_wait(&sm.bar[s], (phase >> s) & 1u);
+                phase ^= 1u << s;
+            }
+        };
+
+        // ---- hand the block to the walker
+        if (lane == 0) {
+            st_vol_u32(&sm.phase_bits, phase);
+            st_vol_u32(&sm.limit_al, limit_al);
+            st_vol_u32(&sm.nchunks, nchunks);
+            st_vol_u32(&sm.shift, shift);
+        }
+        issue_upto(kChunks);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); st_vol_u32(&sm.ready, (uint32_t)b + 1u); }
+        wait_upto(1);
+
+        auto rb = [&](uint32_t k) -> uint32_t { return iring[k & kInMask]; };    // k counts from the aligned start
+        uint32_t size = rb(shift) | (rb(shift + 1u) << 8) | (rb(shift + 2u) << 16);   // tsq_decode.cpp:49-51
+        const bool ok = size <= kBlockMax && size <= a.ostride && nchunks != 0;
+        if (!ok) size = 0;
+        if (lane == 0) a.osizes[b] = size;
+
+        // output positions are kept in "q" coordinates: q = position + (address of the block's
+        // output & 15), so that 16-byte units of the ring are 16-byte units of HBM
+        uint8_t* o = a.out + b * a.ostride;
+        const uint32_t oal = (uint32_t)(reinterpret_cast<uintptr_t>(o) & 15u);
+        uint8_t* o_al = o - oal;
+        uint32_t F = oal;                                                        // flushed up to here (q)
+
+        auto flush = [&](uint32_t E, bool final) {                               // E in q coordinates
+            if (!final) E &= ~15u;
+            if (F >= E) return;
+            if (F & 15u) {                                                       // unaligned head of the block
+                const uint32_t h = min(E, (F + 15u) & ~15u);
+                if (lane < h - F) o_al[F + lane] = oring[(F + lane) & kOMask];
+                F = h;
+            }
+            const uint32_t nvec = (E - F) >> 4;
+            for (uint32_t u = lane; u < nvec; u += 32u) {
+                const uint4 x = *reinterpret_cast<const uint4*>(oring + ((F + 16u * u) & kOMask));
+                *reinterpret_cast<uint4*>(o_al + F + 16u * u) = x;
+            }
+            F += nvec * 16u;
+            if (F < E) {                                                         // final tail
+                if (lane < E - F) o_al[F + lane] = oring[(F + lane) & kOMask];
+                F = E;
+            }
+        };
+
+        const uint32_t pi = lane >> 1, half = lane & 1u;
+        bool done = false;
+        while (!done) {
+            // ---- wait for 16 descriptors, or for the END marker (always the last one published for a block)
+            uint32_t np;
+            uint2 d;
+            for (;;) {
+                const uint32_t have = ld_vol_u32(&sm.produced) - kc;
+                if (have > kPairs) { np = kPairs; }
+                else if (have && (ld_vol_u64(&sm.desc[(kc + have - 1u) & kQMask]).x & kDescEnd)) { np = have - 1u; done = true; }
+                else if (have == kPairs) { np = kPairs; }
+                else { __nanosleep(100u + 40u * (kPairs - have)); continue; }
+                d = ld_vol_u64(&sm.desc[(kc + pi) & kQMask]);
+                // every descriptor carries the lap it was written in: a stale slot can never be mistaken for a fresh one
+                const bool valid = pi > np || ((d.x >> kTagShift) & 3u) == (((kc + pi) / kQueue) & 3u);
+                if (__all_sync(FULL, valid)) break;
+                done = false;
+            }
+            uint32_t jend = __shfl_sync(FULL, d.y, min(np, kPairs - 1u) * 2u);    // END descriptor carries the final j
+            if (np) {
+                // stream bytes of these pairs are resident (the walker saw them); observe the barriers
+                const uint32_t plast = __shfl_sync(FULL, d.x & 0xFFFFFFu, (np - 1u) * 2u);
+                wait_upto((plast + kLook - 2u) / kChunk + 1u);
+
+                // ---- one lane per symbol
+                bool active = pi < np;
+                uint32_t len = 0, q = 0, sp = 0, srcq = 0;
+                bool lit = true;
+                const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y;
+                {
+                    const uint32_t nib = rb(pp);
+                    const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+                    const bool l0 = (d.x & (0x80u << 18)) != 0, l1 = (d.x & (0x40u << 18)) != 0;
+                    uint32_t dst;
+                    if (half == 0) { lit = l0; len = n0 + 1u; sp = pp + 1u; dst = jp; }
+                    else { lit = l1; len = n1 + 1u; sp = pp + 1u + (l0 ? n0 + 1u : 2u); dst = jp + n0 + 1u; }
+                    active = active && dst < size;
+                    len = active ? min(len, size - dst) : 0u;
+                    q = dst + oal;
+                    if (active && !lit) {
+                        const uint32_t off = rb(sp) | (rb(sp + 1u) << 8);        // :69,73,82
+                        active = off <= jp;                                      // corrupt stream guard
+                        srcq = jp - off + oal;
+                    }
+                }
+                const uint32_t J0 = __shfl_sync(FULL, q, 0);                     // q of the step's first byte
+                const uint32_t J1 = __reduce_max_sync(FULL, active ? q + len : 0u);
+
+                // ---- round 0: literals and matches whose source precedes this step's output
+                uint32_t v[4] = {0, 0, 0, 0};
+                bool now = active && (lit || srcq + len <= J0);
+                bool pending = active && !now;
+                if (now) {
+                    if (lit) load16_ring(iring, kInMask, sp, v);
+                    else if (srcq + OUT_RING >= J1 + 16u) load16_ring(oring, kOMask, srcq, v);
+                    else {
+                        // far match: the bytes were flushed to HBM by an earlier step
+                        const uintptr_t ad = reinterpret_cast<uintptr_t>(o_al + srcq);
+                        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+                        const uint32_t sh = (uint32_t)(ad & 3u) * 8u;
+                        uint32_t w[5];
+#pragma unroll
+                        for (int m = 0; m < 5; m++)                              // never touch a word past the source
+                            w[m] = ((uint32_t)(ad & 3u) + len > 4u * m) ? __ldcg(g32 + m) : 0u;
+#pragma unroll
+                        for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
+                    }
+                }
+                {
+                    // reconverge before the ordered stores; take the wrap-safe path for the whole warp if any lane wraps
+                    const bool wrap = __any_sync(FULL, now && ((q & kOMask) + 16u > OUT_RING));
+                    if (now) store16_desc(oring, kOMask, q, v, wrap);
+                }
+                // ---- follow-up rounds: sources inside this step's output
+                uint32_t pm = __ballot_sync(FULL, pending);
+                while (pm) {
+                    __syncwarp();                                                // stores above are visible to the warp
+                    // every pending symbol whose source ends before the first pending pair is now safe; that
+                    // pair itself is always released (its sources precede its own start in every valid
+                    // stream; releasing it unconditionally also bounds the loop on corrupt input)
+                    const uint32_t firstlane = (uint32_t)__ffs((int)pm) - 1u;
+                    const uint32_t frontier = __shfl_sync(FULL, q, firstlane & ~1u);   // even lane's q == start of that pair
+                    now = pending && (srcq + len <= frontier || (lane >> 1) == (firstlane >> 1));
+                    pending = pending && !now;
+                    if (now) {
+                        load16_ring(oring, kOMask, srcq, v);
+                        store_exact(oring, kOMask, q, v, len);
+                    }
+                    pm = __ballot_sync(FULL, pending);
+                }
+                __syncwarp();
+                flush(min(J1, size + oal), false);
+                kc += np;
+                // recycle the stream ring behind this step
+                issue_upto((__shfl_sync(FULL, pp, 0)) / kChunk + kChunks);
+                if (lane == 0) st_vol_u32(&sm.consumed, kc + (done ? 1u : 0u));
+            }
+            if (done) {
+                kc += 1u;                                                        // the END descriptor
+                __syncwarp();
+                flush(min(jend, size) + oal, true);
+                if (lane == 0) st_vol_u32(&sm.consumed, kc);
+            }
+        }
+        wait_upto(issued);                                                       // drain before the ring is reused
+        __syncwarp();
+    }
+}
+
+template <uint32_t OUT_RING>
+__global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uint32_t nslots)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    SlotSmem<OUT_RING>* slots = reinterpret_cast<SlotSmem<OUT_RING>*>(smem_raw);
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned wid  = threadIdx.x >> 5;
+
+    // the walkers are the LAST warps: the warp arbiter favours the highest warp ids
+    if (wid < nslots) {
+        SlotSmem<OUT_RING>& sm = slots[wid];
+        for (uint32_t q = lane; q < kQueue; q += 32u) sm.desc[q] = make_uint2(3u << kTagShift, 0u);
+        if (lane == 0) {
+            for (uint32_t q = 0; q < kChunks; q++) mbar_init(&sm.bar[q], 1);
+            sm.ready = 0; sm.consumed = 0; sm.produced = 0;
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
+    __syncthreads();
+    if (wid < nslots) copier<OUT_RING>(a, slots[wid], wid, nslots, lane);
+    else              walker<OUT_RING>(a, slots, nslots, wid - nslots, lane);
+}
+
+template <uint32_t OUT_RING>
+cudaError_t launch_split_t(const DecodeArgs& a, uint32_t nslots, unsigned ctas, cudaStream_t st)
+{
+    const size_t smem = sizeof(SlotSmem<OUT_RING>) * nslots;
+    cudaError_t e = cudaFuncSetAttribute(decode_split_kernel<OUT_RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    decode_split_kernel<OUT_RING><<<ctas, (nslots + kWalkers) * 32, smem, st>>>(a, nslots);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// One CTA per SM; every CTA owns `nslots` block slots (copier warps) and kWalkers walker warps.
+cudaError_t launch_decode_split(const DecodeArgs& a, int sm_count, cudaStream_t st)
+{
+    if (a.nb == 0) return cudaSuccess;
+    uint64_t per_sm = (a.nb + sm_count - 1) / sm_count;
+    uint32_t nslots = (uint32_t)(per_sm < kMaxSlots ? per_sm : kMaxSlots);
+    if (nslots == 0) nslots = 1;
+    unsigned ctas = (unsigned)((a.nb + nslots - 1) / nslots);
+    if (ctas > (unsigned)sm_count) ctas = (unsigned)sm_count;
+    // output ring as large as 227 KB of shared memory allows
+    const size_t budget = 227u * 1024u;
+    if (sizeof(SlotSmem<16384>) * nslots <= budget) return launch_split_t<16384>(a, nslots, ctas, st);
+    if (sizeof(SlotSmem<8192>) * nslots <= budget)  return launch_split_t<8192>(a, nslots, ctas, st);
+    if (sizeof(SlotSmem<4096>) * nslots <= budget)  return launch_split_t<4096>(a, nslots, ctas, st);
+    return launch_split_t<2048>(a, nslots, ctas, st);
+}
+
+}  // namespace tsqb
