@@ -41,6 +41,7 @@ constexpr uint32_t kInMask   = kInRing - 1;
 constexpr uint32_t kQueue    = 64;                   // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
 constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
+constexpr uint32_t kSteps    = kQueue / kPairs;      // steps the walker can be ahead
 constexpr uint32_t kLook     = 40;                   // stream bytes one pair can touch (1 + 1 + 16 + 16) + slack
 constexpr uint32_t kWalkers  = 4;                    // walker warps per CTA (one per warp scheduler), slots dealt round-robin
 constexpr uint32_t kMaxSlots = 32 - kWalkers;       // copier warps per CTA (copiers + walkers <= 1024 threads)
@@ -53,7 +54,8 @@ struct __align__(16) SlotSmem {
     uint8_t  in_ring[kInRing];
     uint8_t  out_ring[OUT_RING];
     uint2    desc[kQueue];
-    uint64_t bar[kChunks];
+    uint64_t bar[kChunks];   // stream chunk landed (TMA transaction barriers)
+    uint64_t full[kSteps];   // walker -> copier: one more step of descriptors is complete
     // block hand-over copier -> walker (written before `ready`)
     uint32_t ready;          // block index + 1 the slot is set up for
     uint32_t phase_bits;     // mbarrier parities at block start
@@ -62,7 +64,7 @@ struct __align__(16) SlotSmem {
     uint32_t shift;          // stream start inside its first 16-byte unit
     uint32_t consumed;       // copier -> walker: descriptors consumed so far (running count)
     uint32_t produced;       // walker -> copier: descriptors published so far (running count)
-    uint32_t pad[1 + 12];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
+    uint32_t pad[1 + 4];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,6 +77,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
@@ -158,6 +165,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
     uint32_t p = 0, j = 0, size = 0, limit_al = 0, nchunks = 0, avail = 0, bits = 0;
     uint32_t g = 0, ctl = 0;
     uint32_t k = 0, cons = 0;                      // running descriptor counters (never reset)
+    uint32_t steps = 0;                            // running count of completed steps (16 descriptors, or up to END)
 
     // one pair: tsq_decode.cpp:68-86 without the copies.  CHECK = the block may end inside this pair.
     auto pair_step = [&](uint32_t& pp, bool check) {
@@ -206,6 +214,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     p = pp;
                     g += 4u;
                     st_vol_u32(&sm.produced, k);
+                    if ((g & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
                     continue;
                 }
                 const bool data_ok = p + kLook <= have;
@@ -218,11 +227,13 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                         p = pp;
                         g++;
                         st_vol_u32(&sm.produced, k);
+                        if ((g & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
                     } else {
                         const uint32_t tag = (k << (kTagShift - 6)) & (3u << kTagShift);
                         st_vol_u64(&sm.desc[k & kQMask], make_uint2(kDescEnd | tag, j));
                         k++;
                         st_vol_u32(&sm.produced, k);
+                        mbar_arrive(&sm.full[steps % kSteps]); steps++;            // END closes the (possibly partial) step
                         b += stride_slots;
                         phase = b < a.nb ? P_WAIT : P_DONE;
                     }
@@ -246,41 +257,43 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
 }
 
 // ------------------------------------------------------------------------------------------ copier
-// 16 bytes starting at byte `pos` of a power-of-two ring
-__device__ __forceinline__ void load16_ring(const uint8_t* ring, uint32_t mask, uint32_t pos, uint32_t v[4])
+// 16 bytes starting at byte `pos` of a power-of-two ring that begins at shared address `base`.
+// `wrap` (warp-uniform) = some lane's 20-byte window crosses the end of its ring.
+__device__ __forceinline__ void load16_smem(uint32_t base, uint32_t mask, uint32_t pos, uint32_t v[4], bool wrap)
 {
-    const uint32_t a0 = pos & ~3u, sh = (pos & 3u) * 8u;
-    const uint32_t* r32 = reinterpret_cast<const uint32_t*>(ring);
+    const uint32_t sh = (pos & 3u) * 8u;
     uint32_t w[5];
+    if (!wrap) {
+        const uint32_t ad = base + (pos & mask & ~3u);
 #pragma unroll
-    for (int m = 0; m < 5; m++) w[m] = r32[((a0 + 4u * m) & mask) >> 2];
+        for (int m = 0; m < 5; m++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[m]) : "r"(ad + 4u * m));
+    } else {
+#pragma unroll
+        for (int m = 0; m < 5; m++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[m]) : "r"(base + (((pos & ~3u) + 4u * m) & mask)));
+    }
 #pragma unroll
     for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
 }
 
 // blind 16-byte store, highest byte first (see the header comment).  `wrap` must be warp-uniform:
 // the ordering argument needs every participating lane to execute the same store sequence in lockstep.
-__device__ __forceinline__ void store16_desc(uint8_t* ring, uint32_t mask, uint32_t q, const uint32_t v[4], bool wrap)
+// asm volatile: the compiler must keep the stores in exactly this order.
+template <int T>
+__device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4])
 {
-    // volatile: the compiler must keep the stores in exactly this order
-    const uint32_t r = q & mask;
-    if (!wrap) {
-        volatile uint8_t* d = ring + r;
-#pragma unroll
-        for (int t = 15; t >= 0; t--) d[t] = (uint8_t)(v[t >> 2] >> (8 * (t & 3)));
-    } else {
-        volatile uint8_t* d = ring;
-#pragma unroll
-        for (int t = 15; t >= 0; t--) d[(q + (uint32_t)t) & mask] = (uint8_t)(v[t >> 2] >> (8 * (t & 3)));
-    }
+    asm volatile("st.volatile.shared.u8 [%0+%1], %2;" ::"r"(ad), "n"(T), "r"(v[T >> 2] >> (8 * (T & 3))) : "memory");
+    if constexpr (T > 0) store_bytes_desc<T - 1>(ad, v);
 }
 
-// exact-length store (follow-up rounds: later symbols are already in place)
-__device__ __forceinline__ void store_exact(uint8_t* ring, uint32_t mask, uint32_t q, const uint32_t v[4], uint32_t len)
+__device__ __forceinline__ void store16_desc(uint32_t base, uint32_t mask, uint32_t q, const uint32_t v[4], bool wrap)
 {
+    if (!wrap) {
+        store_bytes_desc<15>(base + (q & mask), v);
+    } else {
 #pragma unroll
-    for (int t = 0; t < 16; t++)
-        if ((uint32_t)t < len) ring[(q + (uint32_t)t) & mask] = (uint8_t)(v[t >> 2] >> (8 * (t & 3)));
+        for (int t = 15; t >= 0; t--)
+            asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(base + ((q + (uint32_t)t) & mask)), "r"(v[t >> 2] >> (8 * (t & 3))) : "memory");
+    }
 }
 
 template <uint32_t OUT_RING>
@@ -288,10 +301,14 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
 {
     constexpr uint32_t kOMask = OUT_RING - 1;
     const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
-    uint32_t phase = 0;                    // bit s: parity the next completion of ring slot s will have
+    uint32_t phase = 0;                    // bit s: parity the next completion of stream ring slot s will have
+    uint32_t fphase = 0;                   // same for the step barriers
     uint32_t kc = 0;                       // running descriptor counter (mirrors the walker's k)
+    uint32_t sc = 0;                       // running step counter (mirrors the walker's `steps`)
     uint8_t* oring = sm.out_ring;
     const uint8_t* iring = sm.in_ring;
+    const uint32_t ibase = smem_u32(sm.in_ring), obase = smem_u32(sm.out_ring);
+    const uint32_t pi = lane >> 1, half = lane & 1u;
 
     for (uint64_t b = (uint64_t)blockIdx.x * nslots + slot; b < a.nb; b += stride_slots) {
         uint32_t limit;
@@ -367,25 +384,19 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
             }
         };
 
-        const uint32_t pi = lane >> 1, half = lane & 1u;
         bool done = false;
         while (!done) {
-            // ---- wait for 16 descriptors, or for the END marker (always the last one published for a block)
-            uint32_t np;
-            uint2 d;
-            for (;;) {
-                const uint32_t have = ld_vol_u32(&sm.produced) - kc;
-                if (have > kPairs) { np = kPairs; }
-                else if (have && (ld_vol_u64(&sm.desc[(kc + have - 1u) & kQMask]).x & kDescEnd)) { np = have - 1u; done = true; }
-                else if (have == kPairs) { np = kPairs; }
-                else { __nanosleep(100u + 40u * (kPairs - have)); continue; }
-                d = ld_vol_u64(&sm.desc[(kc + pi) & kQMask]);
-                // every descriptor carries the lap it was written in: a stale slot can never be mistaken for a fresh one
-                const bool valid = pi > np || ((d.x >> kTagShift) & 3u) == (((kc + pi) / kQueue) & 3u);
-                if (__all_sync(FULL, valid)) break;
-                done = false;
+            // ---- sleep on the step barrier until the walker has completed 16 descriptors or reached END
+            {
+                const uint32_t s = sc % kSteps;
+                mbar_wait(&sm.full[s], (fphase >> s) & 1u);
+                fphase ^= 1u << s;
+                sc++;
             }
-            uint32_t jend = __shfl_sync(FULL, d.y, min(np, kPairs - 1u) * 2u);    // END descriptor carries the final j
+            uint32_t np = min(ld_vol_u32(&sm.produced) - kc, kPairs);
+            const uint2 d = ld_vol_u64(&sm.desc[(kc + min(pi, np - 1u)) & kQMask]);
+            if (__shfl_sync(FULL, d.x, (np - 1u) * 2u) & kDescEnd) { np--; done = true; }
+            const uint32_t jend = __shfl_sync(FULL, d.y, np * 2u < 32u ? np * 2u : 31u);   // END descriptor carries the final j
             if (np) {
                 // stream bytes of these pairs are resident (the walker saw them); observe the barriers
                 const uint32_t plast = __shfl_sync(FULL, d.x & 0xFFFFFFu, (np - 1u) * 2u);
@@ -415,15 +426,20 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 const uint32_t J0 = __shfl_sync(FULL, q, 0);                     // q of the step's first byte
                 const uint32_t J1 = __reduce_max_sync(FULL, active ? q + len : 0u);
 
-                // ---- round 0: literals and matches whose source precedes this step's output
+                // ---- round 0: literals and matches whose source precedes this step's output.
+                // Literals and near matches both come out of shared memory (stream ring / output ring);
+                // far matches read bytes an earlier step flushed to HBM.
                 uint32_t v[4] = {0, 0, 0, 0};
                 bool now = active && (lit || srcq + len <= J0);
                 bool pending = active && !now;
-                if (now) {
-                    if (lit) load16_ring(iring, kInMask, sp, v);
-                    else if (srcq + OUT_RING >= J1 + 16u) load16_ring(oring, kOMask, srcq, v);
-                    else {
-                        // far match: the bytes were flushed to HBM by an earlier step
+                bool placed = false;                                             // v[] holds this symbol's bytes
+                const bool far = now && !lit && srcq + OUT_RING < J1 + 16u;
+                {
+                    const uint32_t fbase = lit ? ibase : obase, fmask = lit ? kInMask : kOMask, fpos = lit ? sp : srcq;
+                    const bool sm_src = now && !far;
+                    const bool wrap = __any_sync(FULL, sm_src && ((fpos & fmask) + 20u > fmask + 1u));
+                    if (sm_src) load16_smem(fbase, fmask, fpos, v, wrap);
+                    if (far) {
                         const uintptr_t ad = reinterpret_cast<uintptr_t>(o_al + srcq);
                         const uint32_t* g32 = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
                         const uint32_t sh = (uint32_t)(ad & 3u) * 8u;
@@ -434,13 +450,14 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
 #pragma unroll
                         for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
                     }
+                    placed = now;
                 }
-                {
-                    // reconverge before the ordered stores; take the wrap-safe path for the whole warp if any lane wraps
-                    const bool wrap = __any_sync(FULL, now && ((q & kOMask) + 16u > OUT_RING));
-                    if (now) store16_desc(oring, kOMask, q, v, wrap);
-                }
-                // ---- follow-up rounds: sources inside this step's output
+                const bool owrap = __any_sync(FULL, active && ((q & kOMask) + 16u > OUT_RING));
+                __syncwarp();                                                    // reconverge before the ordered stores
+                if (placed) store16_desc(obase, kOMask, q, v, owrap);
+                // ---- follow-up rounds: sources inside this step's output.  Every round re-stores ALL placed
+                // symbols in the same descending order, which repairs the garbage tails the newly placed ones
+                // throw onto symbols after them.
                 uint32_t pm = __ballot_sync(FULL, pending);
                 while (pm) {
                     __syncwarp();                                                // stores above are visible to the warp
@@ -451,10 +468,11 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                     const uint32_t frontier = __shfl_sync(FULL, q, firstlane & ~1u);   // even lane's q == start of that pair
                     now = pending && (srcq + len <= frontier || (lane >> 1) == (firstlane >> 1));
                     pending = pending && !now;
-                    if (now) {
-                        load16_ring(oring, kOMask, srcq, v);
-                        store_exact(oring, kOMask, q, v, len);
-                    }
+                    const bool wrap = __any_sync(FULL, now && ((srcq & kOMask) + 20u > OUT_RING));
+                    if (now) load16_smem(obase, kOMask, srcq, v, wrap);
+                    placed = placed || now;
+                    __syncwarp();
+                    if (placed) store16_desc(obase, kOMask, q, v, owrap);
                     pm = __ballot_sync(FULL, pending);
                 }
                 __syncwarp();
@@ -462,14 +480,13 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 kc += np;
                 // recycle the stream ring behind this step
                 issue_upto((__shfl_sync(FULL, pp, 0)) / kChunk + kChunks);
-                if (lane == 0) st_vol_u32(&sm.consumed, kc + (done ? 1u : 0u));
             }
             if (done) {
                 kc += 1u;                                                        // the END descriptor
                 __syncwarp();
                 flush(min(jend, size) + oal, true);
-                if (lane == 0) st_vol_u32(&sm.consumed, kc);
             }
+            if (lane == 0) st_vol_u32(&sm.consumed, kc);
         }
         wait_upto(issued);                                                       // drain before the ring is reused
         __syncwarp();
@@ -490,6 +507,7 @@ __global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uin
         for (uint32_t q = lane; q < kQueue; q += 32u) sm.desc[q] = make_uint2(3u << kTagShift, 0u);
         if (lane == 0) {
             for (uint32_t q = 0; q < kChunks; q++) mbar_init(&sm.bar[q], 1);
+            for (uint32_t q = 0; q < kSteps; q++) mbar_init(&sm.full[q], 1);
             sm.ready = 0; sm.consumed = 0; sm.produced = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
