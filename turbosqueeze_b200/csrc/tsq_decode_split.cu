@@ -46,8 +46,6 @@ constexpr uint32_t kLook     = 40;                   // stream bytes one pair ca
 constexpr uint32_t kWalkers  = 4;                    // walker warps per CTA (one per warp scheduler), slots dealt round-robin
 constexpr uint32_t kMaxSlots = 32 - kWalkers;       // copier warps per CTA (copiers + walkers <= 1024 threads)
 
-constexpr uint32_t kDescEnd  = 0x80000000u;
-constexpr uint32_t kTagShift = 26;
 
 template <uint32_t OUT_RING>
 struct __align__(16) SlotSmem {
@@ -62,9 +60,11 @@ struct __align__(16) SlotSmem {
     uint32_t limit_al;       // readable stream bytes, counted from the 16-byte aligned start
     uint32_t nchunks;
     uint32_t shift;          // stream start inside its first 16-byte unit
-    uint32_t consumed;       // copier -> walker: descriptors consumed so far (running count)
-    uint32_t produced;       // walker -> copier: descriptors published so far (running count)
-    uint32_t pad[1 + 4];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
+    uint32_t consumed;       // copier -> walker: descriptors of this block consumed so far
+    uint32_t produced;       // walker -> copier: descriptors of this block published so far
+    uint32_t ended;          // walker -> copier: the walk of this block is complete (set after the last `produced`)
+    uint32_t end_j;          // output position the walk stopped at
+    uint32_t pad[3];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,11 +102,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
@@ -135,11 +135,6 @@ __device__ __forceinline__ uint2 ld_vol_u64(const uint2* p)
     return v;
 }
 
-__device__ __forceinline__ void st_vol_u64(uint2* p, uint2 v)
-{
-    asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(smem_u32(p)), "r"(v.x), "r"(v.y) : "memory");
-}
-
 // where block b's stream starts / how many bytes of it may be read
 __device__ __forceinline__ const uint8_t* stream_of(const DecodeArgs& a, uint64_t b, uint32_t& limit)
 {
@@ -160,27 +155,20 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
     uint64_t b = (uint64_t)blockIdx.x * nslots + slot;
     uint32_t phase = (slot < nslots && b < a.nb) ? P_WAIT : P_DONE;
     SlotSmem<OUT_RING>& sm = slots[slot < nslots ? slot : 0];
-    const uint8_t* ring = sm.in_ring;
 
     uint32_t p = 0, j = 0, size = 0, limit_al = 0, nchunks = 0, avail = 0, bits = 0;
-    uint32_t g = 0, ctl = 0;
-    uint32_t k = 0, cons = 0;                      // running descriptor counters (never reset)
-    uint32_t steps = 0;                            // running count of completed steps (16 descriptors, or up to END)
+    uint32_t ctl = 0;
+    uint32_t k = 0, cons = 0;                      // descriptors of the current block written / known consumed
+    uint32_t steps = 0;                            // running count of completed steps (16 descriptors, or up to the end)
+    const uint32_t rbase = smem_u32(sm.in_ring), dbase = smem_u32(sm.desc);
 
-    // one pair: tsq_decode.cpp:68-86 without the copies.  CHECK = the block may end inside this pair.
-    auto pair_step = [&](uint32_t& pp, bool check) {
-        const uint32_t nib = ring[pp & kInMask];                                    // :68
-        const uint32_t tag = (k << (kTagShift - 6)) & (3u << kTagShift);            // ((k / kQueue) & 3) << kTagShift
-        st_vol_u64(&sm.desc[k & kQMask], make_uint2(pp | ((ctl & 0xC0u) << 18) | tag, j));
-        const uint32_t n0 = nib >> 4, n1 = nib & 15u;
-        const uint32_t pay0 = (ctl & 0x80u) ? n0 + 1u : 2u;
-        const uint32_t pay1 = (ctl & 0x40u) ? n1 + 1u : 2u;
-        ctl <<= 2;
-        const uint32_t j1 = j + n0 + 1u;
-        const bool two = !check || j1 < size;                                       // second symbol exists
-        pp = pp + 1u + pay0 + (two ? pay1 : 0u);
-        j = j1 + (two ? n1 + 1u : 0u);
-        k++;
+    auto ring_u8 = [&](uint32_t pos) -> uint32_t {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(rbase + (pos & kInMask)));
+        return v;
+    };
+    auto put_desc = [&](uint32_t ad, uint32_t x, uint32_t y) {
+        asm volatile("st.volatile.shared.v2.u32 [%0], {%1, %2};" ::"r"(ad), "r"(x), "r"(y) : "memory");
     };
 
     for (;;) {
@@ -195,50 +183,62 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                 // the 3-byte header needs the first chunk (tsq_decode.cpp:49-53)
                 if (size == 0xffffffffu) {
                     if (avail >= 1u || avail == nchunks) {
-                        const uint32_t s0 = p;
-                        size = (uint32_t)ring[s0 & kInMask] | ((uint32_t)ring[(s0 + 1u) & kInMask] << 8) | ((uint32_t)ring[(s0 + 2u) & kInMask] << 16);
+                        size = ring_u8(p) | (ring_u8(p + 1u) << 8) | (ring_u8(p + 2u) << 16);
                         if (!(size <= kBlockMax && size <= a.ostride) || nchunks == 0) size = 0;
-                        p = s0 + 3u;
+                        p += 3u;
                     }
                     continue;
                 }
                 const uint32_t have = (avail == nchunks) ? 0xffffffffu : avail * kChunk;
-                // a whole group (control byte + 4 full pairs) with no end-of-block inside it
-                const bool fast = (g & 3u) == 0 && p + 4u * kLook <= have && (k - cons) + 4u <= kQueue &&
-                                  j + 128u < size && p + 4u * kLook <= limit_al;
-                if (fast) {
+                if ((k - cons) + 4u > kQueue) cons = ld_vol_u32(&sm.consumed);
+                // ---- fast path: a whole group (control byte + 4 full pairs, tsq_decode.cpp:62-86) with no
+                // end-of-block inside it.  k % 4 == 0 here, so the 4 descriptors are contiguous in the queue.
+                if ((k & 3u) == 0 && p + 4u * kLook <= have && (k - cons) + 4u <= kQueue && j + 128u < size &&
+                    p + 4u * kLook <= limit_al) {
+                    const uint32_t dsl = dbase + ((k & kQMask) << 3);
+                    const uint32_t c = ring_u8(p);                                  // :62
                     uint32_t pp = p + 1u;
-                    ctl = ring[p & kInMask];                                        // tsq_decode.cpp:62
 #pragma unroll
-                    for (int q = 0; q < 4; q++) pair_step(pp, false);
+                    for (int q = 0; q < 4; q++) {
+                        const uint32_t nib = ring_u8(pp);                           // :68
+                        put_desc(dsl + 8u * q, pp | ((c << (18 + 2 * q)) & 0x3000000u), j);
+                        const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+                        const uint32_t pay0 = (c & (0x80u >> (2 * q))) ? n0 + 2u : 3u;   // payload + the size byte itself
+                        const uint32_t pay1 = (c & (0x40u >> (2 * q))) ? n1 + 1u : 2u;
+                        pp += pay0 + pay1;
+                        j += n0 + n1 + 2u;
+                    }
                     p = pp;
-                    g += 4u;
+                    k += 4u;
                     st_vol_u32(&sm.produced, k);
-                    if ((g & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
+                    if ((k & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
                     continue;
                 }
-                const bool data_ok = p + kLook <= have;
-                const bool room    = (k - cons) < kQueue;
-                if (data_ok && room) {
-                    if (j < size && p < limit_al) {
-                        uint32_t pp = p;
-                        if ((g & 3u) == 0) { ctl = ring[pp & kInMask]; pp++; }
-                        pair_step(pp, true);
-                        p = pp;
-                        g++;
-                        st_vol_u32(&sm.produced, k);
-                        if ((g & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
-                    } else {
-                        const uint32_t tag = (k << (kTagShift - 6)) & (3u << kTagShift);
-                        st_vol_u64(&sm.desc[k & kQMask], make_uint2(kDescEnd | tag, j));
-                        k++;
-                        st_vol_u32(&sm.produced, k);
-                        mbar_arrive(&sm.full[steps % kSteps]); steps++;            // END closes the (possibly partial) step
-                        b += stride_slots;
-                        phase = b < a.nb ? P_WAIT : P_DONE;
-                    }
+                // ---- slow path: one pair, or the end of the block
+                if (!(p + kLook <= have)) continue;
+                if (!((k - cons) < kQueue)) { cons = ld_vol_u32(&sm.consumed); continue; }
+                if (j < size && p < limit_al) {
+                    uint32_t pp = p;
+                    const uint32_t q = k & 3u;
+                    if (q == 0) { ctl = ring_u8(pp); pp++; }
+                    const uint32_t nib = ring_u8(pp);
+                    put_desc(dbase + ((k & kQMask) << 3), pp | ((ctl << (18u + 2u * q)) & 0x3000000u), j);
+                    const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+                    const uint32_t pay0 = (ctl & (0x80u >> (2u * q))) ? n0 + 1u : 2u;
+                    const uint32_t pay1 = (ctl & (0x40u >> (2u * q))) ? n1 + 1u : 2u;
+                    const uint32_t j1 = j + n0 + 1u;
+                    const bool two = j1 < size;                                     // second symbol exists
+                    p = pp + 1u + pay0 + (two ? pay1 : 0u);
+                    j = j1 + (two ? n1 + 1u : 0u);
+                    k++;
+                    st_vol_u32(&sm.produced, k);
+                    if ((k & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
                 } else {
-                    if (!room || (k - cons) + 4u > kQueue) cons = ld_vol_u32(&sm.consumed);
+                    st_vol_u32(&sm.end_j, j);
+                    st_vol_u32(&sm.ended, 1u);
+                    mbar_arrive(&sm.full[steps % kSteps]); steps++;                 // closes the last (possibly empty) step
+                    b += stride_slots;
+                    phase = b < a.nb ? P_WAIT : P_DONE;
                 }
             } else if (phase == P_WAIT) {
                 if (ld_vol_u32(&sm.ready) == (uint32_t)b + 1u) {
@@ -247,7 +247,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     limit_al = ld_vol_u32(&sm.limit_al);
                     nchunks  = ld_vol_u32(&sm.nchunks);
                     p        = ld_vol_u32(&sm.shift);
-                    avail = 0; g = 0; ctl = 0; j = 0; size = 0xffffffffu;
+                    avail = 0; ctl = 0; j = 0; k = 0; cons = 0; size = 0xffffffffu;
                     phase = P_WALK;
                 }
             }
@@ -303,7 +303,6 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
     const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
     uint32_t phase = 0;                    // bit s: parity the next completion of stream ring slot s will have
     uint32_t fphase = 0;                   // same for the step barriers
-    uint32_t kc = 0;                       // running descriptor counter (mirrors the walker's k)
     uint32_t sc = 0;                       // running step counter (mirrors the walker's `steps`)
     uint8_t* oring = sm.out_ring;
     const uint8_t* iring = sm.in_ring;
@@ -340,7 +339,11 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
         };
 
         // ---- hand the block to the walker
+        uint32_t kc = 0;                                                         // descriptors of this block consumed
         if (lane == 0) {
+            st_vol_u32(&sm.produced, 0u);
+            st_vol_u32(&sm.consumed, 0u);
+            st_vol_u32(&sm.ended, 0u);
             st_vol_u32(&sm.phase_bits, phase);
             st_vol_u32(&sm.limit_al, limit_al);
             st_vol_u32(&sm.nchunks, nchunks);
@@ -393,10 +396,10 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 fphase ^= 1u << s;
                 sc++;
             }
-            uint32_t np = min(ld_vol_u32(&sm.produced) - kc, kPairs);
-            const uint2 d = ld_vol_u64(&sm.desc[(kc + min(pi, np - 1u)) & kQMask]);
-            if (__shfl_sync(FULL, d.x, (np - 1u) * 2u) & kDescEnd) { np--; done = true; }
-            const uint32_t jend = __shfl_sync(FULL, d.y, np * 2u < 32u ? np * 2u : 31u);   // END descriptor carries the final j
+            // a step is 16 descriptors, except the last one of a block (fewer, possibly none)
+            const uint32_t np = min(ld_vol_u32(&sm.produced) - kc, kPairs);
+            done = np < kPairs;
+            const uint2 d = ld_vol_u64(&sm.desc[(kc + pi) & kQMask]);
             if (np) {
                 // stream bytes of these pairs are resident (the walker saw them); observe the barriers
                 const uint32_t plast = __shfl_sync(FULL, d.x & 0xFFFFFFu, (np - 1u) * 2u);
@@ -482,9 +485,8 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 issue_upto((__shfl_sync(FULL, pp, 0)) / kChunk + kChunks);
             }
             if (done) {
-                kc += 1u;                                                        // the END descriptor
                 __syncwarp();
-                flush(min(jend, size) + oal, true);
+                flush(min(ld_vol_u32(&sm.end_j), size) + oal, true);
             }
             if (lane == 0) st_vol_u32(&sm.consumed, kc);
         }
@@ -504,11 +506,10 @@ __global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uin
     // the walkers are the LAST warps: the warp arbiter favours the highest warp ids
     if (wid < nslots) {
         SlotSmem<OUT_RING>& sm = slots[wid];
-        for (uint32_t q = lane; q < kQueue; q += 32u) sm.desc[q] = make_uint2(3u << kTagShift, 0u);
         if (lane == 0) {
             for (uint32_t q = 0; q < kChunks; q++) mbar_init(&sm.bar[q], 1);
             for (uint32_t q = 0; q < kSteps; q++) mbar_init(&sm.full[q], 1);
-            sm.ready = 0; sm.consumed = 0; sm.produced = 0;
+            sm.ready = 0; sm.consumed = 0; sm.produced = 0; sm.ended = 0;
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
     }
