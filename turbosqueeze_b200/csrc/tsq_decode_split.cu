@@ -96,7 +96,7 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parity)
 {
     asm volatile(
         "{\n\t"
@@ -106,7 +106,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+        "}" ::"r"(bar_addr), "r"(parity), "r"(1000000u) : "memory");
 }
 
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
@@ -193,8 +193,10 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                 if ((k - cons) + 4u > kQueue) cons = ld_vol_u32(&sm.consumed);
                 // ---- fast path: a whole group (control byte + 4 full pairs, tsq_decode.cpp:62-86) with no
                 // end-of-block inside it.  k % 4 == 0 here, so the 4 descriptors are contiguous in the queue.
-                if ((k & 3u) == 0 && p + 4u * kLook <= have && (k - cons) + 4u <= kQueue && j + 128u < size &&
-                    p + 4u * kLook <= limit_al) {
+                const uint32_t p_safe = min(have, limit_al);
+                int groups = 0;
+#pragma unroll 1
+                while (groups < 4 && (k & 3u) == 0 && p + 4u * kLook <= p_safe && (k - cons) + 4u <= kQueue && j + 128u < size) {
                     const uint32_t dsl = dbase + ((k & kQMask) << 3);
                     const uint32_t c = ring_u8(p);                                  // :62
                     uint32_t pp = p + 1u;
@@ -212,8 +214,9 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     k += 4u;
                     st_vol_u32(&sm.produced, k);
                     if ((k & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
-                    continue;
+                    groups++;
                 }
+                if (groups) continue;
                 // ---- slow path: one pair, or the end of the block
                 if (!(p + kLook <= have)) continue;
                 if (!((k - cons) < kQueue)) { cons = ld_vol_u32(&sm.consumed); continue; }
@@ -307,6 +310,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
     uint8_t* oring = sm.out_ring;
     const uint8_t* iring = sm.in_ring;
     const uint32_t ibase = smem_u32(sm.in_ring), obase = smem_u32(sm.out_ring);
+    const uint32_t bar_base = smem_u32(sm.bar), full_base = smem_u32(sm.full);
     const uint32_t pi = lane >> 1, half = lane & 1u;
 
     for (uint64_t b = (uint64_t)blockIdx.x * nslots + slot; b < a.nb; b += stride_slots) {
@@ -317,7 +321,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
         const uint32_t limit_al = shift + limit;
         const uint32_t total_al = (limit_al + 15u) & ~15u;
         const uint32_t nchunks = (total_al + kChunk - 1) / kChunk;
-        uint32_t issued = 0, waited = 0;
+        uint32_t issued = 0, waited = 0, cur_chunk = 0;
 
         auto issue_upto = [&](uint32_t want) {                                   // all lanes call; lane 0 copies
             want = min(want, nchunks);
@@ -333,7 +337,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
             want = min(want, issued);
             for (; waited < want; waited++) {
                 const uint32_t s = waited % kChunks;
-                mbar_wait(&sm.bar[s], (phase >> s) & 1u);
+                mbar_wait_addr(bar_base + 8u * s, (phase >> s) & 1u);
                 phase ^= 1u << s;
             }
         };
@@ -367,6 +371,15 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
         uint8_t* o_al = o - oal;
         uint32_t F = oal;                                                        // flushed up to here (q)
 
+        // complete 16-byte units of the ring -> HBM, one 128-bit load/store per lane
+        auto flush_units = [&](uint32_t E) {                                     // E 16-byte aligned, F 16-byte aligned
+            for (uint32_t at = F + 16u * lane; at < E; at += 512u) {
+                uint4 x;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
+                *reinterpret_cast<uint4*>(o_al + at) = x;
+            }
+            F = E;
+        };
         auto flush = [&](uint32_t E, bool final) {                               // E in q coordinates
             if (!final) E &= ~15u;
             if (F >= E) return;
@@ -375,12 +388,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 if (lane < h - F) o_al[F + lane] = oring[(F + lane) & kOMask];
                 F = h;
             }
-            const uint32_t nvec = (E - F) >> 4;
-            for (uint32_t u = lane; u < nvec; u += 32u) {
-                const uint4 x = *reinterpret_cast<const uint4*>(oring + ((F + 16u * u) & kOMask));
-                *reinterpret_cast<uint4*>(o_al + F + 16u * u) = x;
-            }
-            F += nvec * 16u;
+            flush_units(E & ~15u);
             if (F < E) {                                                         // final tail
                 if (lane < E - F) o_al[F + lane] = oring[(F + lane) & kOMask];
                 F = E;
@@ -392,7 +400,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
             // ---- sleep on the step barrier until the walker has completed 16 descriptors or reached END
             {
                 const uint32_t s = sc % kSteps;
-                mbar_wait(&sm.full[s], (fphase >> s) & 1u);
+                mbar_wait_addr(full_base + 8u * s, (fphase >> s) & 1u);
                 fphase ^= 1u << s;
                 sc++;
             }
@@ -403,7 +411,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
             if (np) {
                 // stream bytes of these pairs are resident (the walker saw them); observe the barriers
                 const uint32_t plast = __shfl_sync(FULL, d.x & 0xFFFFFFu, (np - 1u) * 2u);
-                wait_upto((plast + kLook - 2u) / kChunk + 1u);
+                if ((plast + kLook - 2u) / kChunk >= waited) wait_upto((plast + kLook - 2u) / kChunk + 1u);
 
                 // ---- one lane per symbol
                 bool active = pi < np;
@@ -479,10 +487,11 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                     pm = __ballot_sync(FULL, pending);
                 }
                 __syncwarp();
-                flush(min(J1, size + oal), false);
+                if (F & 15u) flush(J1, false); else if ((J1 & ~15u) > F) flush_units(J1 & ~15u);
                 kc += np;
                 // recycle the stream ring behind this step
-                issue_upto((__shfl_sync(FULL, pp, 0)) / kChunk + kChunks);
+                const uint32_t c0 = __shfl_sync(FULL, pp, 0) / kChunk;
+                if (c0 != cur_chunk) { cur_chunk = c0; issue_upto(c0 + kChunks); }
             }
             if (done) {
                 __syncwarp();
