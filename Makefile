@@ -6,7 +6,7 @@ PKG    := turbosqueeze_b200
 CSRC   := $(PKG)/csrc
 ARCH   := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unused-function
-CU     := $(CSRC)/tsq_decode.cu $(CSRC)/tsq_decode_warp.cu $(CSRC)/tsq_decode_split.cu $(CSRC)/tsq_encode_scalar.cu $(CSRC)/tsq_encode_warp.cu $(CSRC)/tsq_container.cu $(CSRC)/tsq_capi.cu
+CU     := $(CSRC)/tsq_decode.cu $(CSRC)/tsq_decode_warp.cu $(CSRC)/tsq_decode_split.cu $(CSRC)/tsq_encode_scalar.cu $(CSRC)/tsq_encode_warp.cu $(CSRC)/tsq_encode_batch.cu $(CSRC)/tsq_container.cu $(CSRC)/tsq_capi.cu
 OBJ    := $(CU:.cu=.o)
 HDR    := $(wildcard $(CSRC)/*.cuh) include/tsq_b200.h
 

@@ -73,7 +73,7 @@ void tsqb_destroy(tsqb_context* ctx);
 uint64_t tsqb_slot_stride(uint32_t block_size);
 
 /* Kernel selection knobs (for benchmarking / tests).  key: "encode_impl" (0 = auto, 1 = scalar
- * thread-per-block, 2 = warp-per-block), "decode_lanes" (0 = auto, else 1,2,4,8,16,32 lanes per
+ * thread-per-block, 2 = warp-per-block byte emitter, 3 = warp-per-block token batches), "decode_lanes" (0 = auto, else 1,2,4,8,16,32 lanes per
  * block), "encode_slots" (0 = auto: concurrent hash tables).  Returns 0 when the key is known. */
 int tsqb_set_option(tsqb_context* ctx, const char* key, int64_t value);
 

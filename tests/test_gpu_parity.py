@@ -81,7 +81,7 @@ def golden_input(g):
     return buf
 
 
-@pytest.mark.parametrize("impl,ext", [(2, 0), (1, 0), (1, 1)], ids=["warp", "scalar", "scalar-ext"])
+@pytest.mark.parametrize("impl,ext", [(3, 0), (2, 0), (1, 0), (1, 1)], ids=["batch", "warp", "scalar", "scalar-ext"])
 def test_encode_matches_reference_golden_vectors(torch, ctx, impl, ext):
     """tests/golden/golden_blocks.json was produced by the compiled unmodified reference."""
     for g in GOLDEN:
@@ -106,7 +106,7 @@ CASES = [(1, 1), (2, 2), (5, 5), (31, 31), (32, 32), (33, 33), (34, 34), (63, 64
 
 
 @pytest.mark.parametrize("kind", ["text", "random", "rep8", "zeros", "runs"])
-@pytest.mark.parametrize("impl,ext", [(2, 0), (1, 0), (1, 1)], ids=["warp", "scalar", "scalar-ext"])
+@pytest.mark.parametrize("impl,ext", [(3, 0), (2, 0), (1, 0), (1, 1)], ids=["batch", "warp", "scalar", "scalar-ext"])
 def test_encode_bit_exact_vs_oracle(torch, ctx, checker, kind, impl, ext):
     rng = np.random.default_rng(11)
     cases = CASES + [(int(rng.integers(1, 400000)), int(rng.integers(1, 300000))) for _ in range(6)]

@@ -144,7 +144,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     EncodeArgs a;
     a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
-    const int impl = (c->encode_impl == 1 || with_ext) ? 1 : 2;
+    const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
     if (c->tables.ensure((size_t)a.n_slots * kTableBytes)) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
     a.tables = (uint16_t*)c->tables.p;

@@ -8,6 +8,7 @@ namespace tsqb {
 
 cudaError_t launch_encode_scalar(const EncodeArgs& a, bool ext, cudaStream_t st);
 cudaError_t launch_encode_warp(const EncodeArgs& a, cudaStream_t st);
+cudaError_t launch_encode_batch(const EncodeArgs& a, cudaStream_t st);
 
 uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override)
 {
@@ -23,7 +24,8 @@ uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_over
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int /*sm_count*/, cudaStream_t st)
 {
     if (impl == 1 || ext) return launch_encode_scalar(a, ext, st);
-    return launch_encode_warp(a, st);
+    if (impl == 2) return launch_encode_warp(a, st);
+    return launch_encode_batch(a, st);
 }
 
 // ---- pack: offsets = exclusive scan of (3 + size), one CTA (n_blocks is at most a few million)

@@ -34,7 +34,8 @@ struct DecodeArgs {
     uint32_t*       osizes;
 };
 
-// encode_impl: 1 = scalar (one thread per block), 2 = warp per block.
+// encode_impl: 1 = scalar (one thread per block), 2 = warp per block (byte-at-a-time emitter),
+// 3 = warp per block with token batches (tsq_encode_batch.cu, the default without extensions).
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int sm_count, cudaStream_t st);
 // how many hash tables launch_encode(impl) will use for nb blocks (caller sizes a.tables from it)
 uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);

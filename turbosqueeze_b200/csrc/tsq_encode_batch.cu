@@ -1,0 +1,450 @@
+// tsq_encode_batch.cu -- the production no-extension encoder: one WARP per block, decisions first,
+// bytes later.
+//
+// Reference semantics: tsqEncodeNoext (tsq_encode.cpp:48-189); bit-exact, see SURVEY.md 8(a).
+//
+// The greedy parse is a serial chain (every probe reads a table entry written by an earlier probe,
+// tsq_encode.cpp:74-79), so the warp spends its time in a warp-uniform decision loop.  This kernel
+// keeps that loop free of memory traffic and of byte shuffling:
+//
+//   1. WINDOW PRECOMPUTE (parallel, lane L <-> position base + L): the 4-byte word and hash, the
+//      table entry as committed before the window, the candidate's 16 bytes and hence the match
+//      length against it (capped at 16, tsq_encode.cpp:126-137).  All of this is independent of the
+//      parse, so every global load of the window is issued at once.  Positions of the window with
+//      the same hash are found with __match_any_sync; the decision loop redirects a probe to the
+//      nearest earlier lane that was really inserted ("last writer wins", :79).
+//   2. DECISION LOOP (warp-uniform): first hit of a literal scan = ballot + ffs; match length =
+//      one shuffle of the precomputed length, then the clamps of :139-145; the probe that follows a
+//      match (:162-170) is another lane of the same window.  The loop only appends TOKENS
+//      (literal run <= 16 bytes / match) to a small shared-memory queue and tracks the input
+//      position at the start of the open pair (rep_last_i).
+//   3. EMISSION (parallel, lane s <-> token s, 32 tokens at a time): the layout of the stream is a
+//      pure function of the tokens -- symbol s of a batch that starts at byte Bj sits at
+//      Bj + (s/8 + 1) control bytes + (s/2 + 1) size bytes + the payload bytes before it
+//      (:57-61,94-95,157-159) -- so one warp prefix sum places all 32 payloads; control bytes are a
+//      ballot, size bytes a shuffle.  Payloads are staged in a shared-memory ring (literals as blind
+//      16-byte runs stored highest byte first, so a run's garbage tail is overwritten by the bytes
+//      that belong there, exactly what the reference's blind tsq_memcpy16 does serially, :88,108)
+//      and leave for HBM as coalesced 128-bit stores.
+//   4. The inserts of the window are committed to the table (global memory, one table per block in
+//      flight) when the window is left.
+//
+// Nothing is stored past the returned size; the two trailing never-initialised bytes of the
+// reference (:176-188) are reproduced as in tsq_encode_common.cuh.
+#include "tsq_encode_common.cuh"
+
+namespace tsqb {
+
+namespace {
+
+constexpr unsigned FULL   = 0xffffffffu;
+constexpr uint32_t kTok   = 64;                      // token queue entries per warp
+constexpr uint32_t kORing = 1024;                    // output staging ring per warp (bytes)
+constexpr uint32_t kOMask = kORing - 1;
+constexpr int      kWarps = 4;                       // warps (= blocks in flight) per CTA
+
+// token: bit 31 = literal, bits 27..30 = length - 1, low bits = literal source position / match offset
+constexpr uint32_t kTokLit = 0x80000000u;
+
+struct __align__(16) WarpWs {
+    uint8_t  oring[kORing];
+    uint32_t tok[kTok];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// 16 bytes at an arbitrary address of the (read-only) input
+__device__ __forceinline__ void ldg16(const uint8_t* p, uint32_t v[4])
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3u) * 8u;
+    uint32_t t[5];
+#pragma unroll
+    for (int m = 0; m < 5; m++) t[m] = __ldg(w + m);
+#pragma unroll
+    for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(t[m], t[m + 1], sh);
+}
+
+// number of equal leading bytes of two 16-byte strings (tsq_encode.cpp:126-137)
+__device__ __forceinline__ uint32_t prefix16(const uint32_t a[4], const uint32_t b[4])
+{
+    const uint64_t lo = ((uint64_t)(a[1] ^ b[1]) << 32) | (a[0] ^ b[0]);
+    const uint64_t hi = ((uint64_t)(a[3] ^ b[3]) << 32) | (a[2] ^ b[2]);
+    if (lo) return (uint32_t)(__ffsll((long long)lo) - 1) >> 3;
+    if (hi) return 8u + ((uint32_t)(__ffsll((long long)hi) - 1) >> 3);
+    return 16u;
+}
+
+template <int T>
+__device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4], bool lit)
+{
+    // bytes 2..15 only exist for literal runs; bytes 0..1 also carry a match offset
+    if (T < 2 || lit)
+        asm volatile("st.volatile.shared.u8 [%0+%1], %2;" ::"r"(ad), "n"(T), "r"(v[T >> 2] >> (8 * (T & 3))) : "memory");
+    if constexpr (T > 0) store_bytes_desc<T - 1>(ad, v, lit);
+}
+
+__device__ __forceinline__ uint32_t lanes_from_to(uint32_t lo, uint32_t hi)   // bits lo..hi inclusive
+{
+    return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
+}
+
+struct BlockEncoder {
+    // ---- fixed for the block
+    const uint8_t* __restrict__ in;
+    uint8_t*  o_al;           // output slot, rounded down to 16 bytes
+    uint32_t  oal;            // slot address & 15: ring/flush positions are q = byte offset + oal
+    uint32_t  size;
+    uint32_t  obase, tbase;   // shared addresses of the output ring / token queue
+    unsigned  lane;
+    // ---- parse state (warp-uniform)
+    uint32_t  n;              // symbols decided so far
+    uint32_t  rep;            // input position at the start of the open pair (rep_last_i)
+    uint32_t  th, nt;         // token queue head / count
+    // ---- emission state (warp-uniform)
+    uint32_t  Bj;             // byte offset of the control byte of the next batch's first group
+    uint32_t  F;              // flushed up to here (q coordinates)
+    uint32_t  lit_js, lit_src;// output offset / input position of the last literal run (0x80000000: none)
+
+    __device__ __forceinline__ void push(uint32_t tok)
+    {
+        if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(tbase + (((th + nt) & (kTok - 1)) << 2)), "r"(tok) : "memory");
+        nt++;
+    }
+
+    // tsq_encode.cpp:93-95 / :157-159, the part the parse needs
+    __device__ __forceinline__ void symbol_done(uint32_t in_pos)
+    {
+        n++;
+        if ((n & 1u) == 0) rep = in_pos;
+    }
+
+    // tsq_encode.cpp:85-97 / :105-117 -- pending literals [from, upto) leave as runs of at most 16
+    __device__ __forceinline__ void literals(uint32_t& from, uint32_t upto)
+    {
+        do {
+            uint32_t cnt = upto - from;
+            if (cnt > 16u) cnt = 16u;
+            push(kTokLit | ((cnt - 1u) << 27) | from);
+            from += cnt;
+            symbol_done(from);
+        } while (upto - from > 0);
+    }
+
+    __device__ __forceinline__ void match(uint32_t offset, uint32_t k, uint32_t in_pos_after)
+    {
+        push(((k - 1u) << 27) | offset);
+        symbol_done(in_pos_after);
+    }
+
+    __device__ __forceinline__ void ring_put(uint32_t q, uint32_t v)
+    {
+        asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + (q & kOMask)), "r"(v) : "memory");
+    }
+
+    __device__ __forceinline__ uint32_t ring_get(uint32_t q)
+    {
+        uint32_t v;
+        asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(v) : "r"(obase + (q & kOMask)) : "memory");
+        return v;
+    }
+
+    // complete 16-byte units below E (q coordinates) -> HBM
+    __device__ __forceinline__ void flush_to(uint32_t E, bool final)
+    {
+        if (!final) E &= ~15u;
+        if (F >= E) return;
+        if (F & 15u) {                                                           // unaligned head of the slot
+            const uint32_t h = min(E, (F + 15u) & ~15u);
+            if (lane < h - F) o_al[F + lane] = (uint8_t)ring_get(F + lane);
+            F = h;
+        }
+        const uint32_t Ev = E & ~15u;
+        for (uint32_t at = F + 16u * lane; at < Ev; at += 512u) {
+            uint4 x;
+            asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)) : "memory");
+            *reinterpret_cast<uint4*>(o_al + at) = x;
+        }
+        if (Ev > F) F = Ev;
+        if (F < E) {                                                             // final tail
+            if (lane < E - F) o_al[F + lane] = (uint8_t)ring_get(F + lane);
+            F = E;
+        }
+    }
+
+    // Emit `cnt` (<= 32) tokens from the head of the queue: lane s places symbol s.
+    // Returns the byte offset just behind the last payload.
+    __device__ uint32_t emit(uint32_t cnt)
+    {
+        __syncwarp();                                                            // tokens visible
+        uint32_t tok = 0;
+        if (lane < cnt) asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(tok) : "r"(tbase + (((th + lane) & (kTok - 1)) << 2)) : "memory");
+        const bool valid = lane < cnt;
+        const bool lit = valid && (tok & kTokLit);
+        const uint32_t nibble = (tok >> 27) & 15u;
+        const uint32_t pl = valid ? (lit ? nibble + 1u : 2u) : 0u;               // payload bytes
+
+        // inclusive warp prefix sum of the payload lengths
+        uint32_t incl = pl;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(FULL, incl, d);
+            if (lane >= (unsigned)d) incl += t;
+        }
+        const uint32_t P = incl - pl;
+        const uint32_t total = __shfl_sync(FULL, incl, 31);
+        const uint32_t pos = Bj + (lane >> 3) + 1u + (lane >> 1) + 1u + P;        // byte offset of this payload
+        const uint32_t q = pos + oal;
+
+        // ---- payloads: literal run = blind 16 bytes, match = 2-byte offset (:152-153)
+        uint32_t v[4] = {tok & 0xFFFFu, 0, 0, 0};
+        if (lit) ldg16(in + (tok & 0x3FFFFFu), v);
+        // the ordering argument needs all lanes in lockstep: one warp-uniform choice of the store path
+        const bool wrap = __any_sync(FULL, valid && ((q & kOMask) + 16u > kORing));
+        __syncwarp();
+        if (valid) {
+            if (!wrap) store_bytes_desc<15>(obase + (q & kOMask), v, lit);
+            else {
+#pragma unroll
+                for (int t = 15; t >= 0; t--)
+                    if (t < 2 || lit) ring_put(q + (uint32_t)t, v[t >> 2] >> (8 * (t & 3)));
+            }
+        }
+        // remember the last literal run for the never-initialised trailing bytes (finish)
+        {
+            const uint32_t lm = __ballot_sync(FULL, lit);
+            if (lm) {
+                const uint32_t L = 31u - (uint32_t)__clz((int)lm);
+                lit_js = __shfl_sync(FULL, pos, L);
+                lit_src = __shfl_sync(FULL, tok & 0x3FFFFFu, L);
+            }
+        }
+        __syncwarp();                                                            // payloads (and their garbage tails) are down
+        // ---- size bytes: one per pair, right before the pair's first payload (:95,159).  A trailing
+        // odd symbol's byte is (nibble << 4) (:183-186).
+        {
+            const uint32_t other = __shfl_down_sync(FULL, nibble, 1);
+            if (valid && !(lane & 1u)) ring_put(q - 1u, (nibble << 4) | ((lane + 1u < cnt) ? other : 0u));
+        }
+        // ---- control bytes: one per 8 symbols, right before the size byte of the group's first pair;
+        // bit (7 - t) = symbol t is a literal (:94,158); a trailing partial group is padded with ones (:176-182)
+        {
+            const uint32_t lm = __ballot_sync(FULL, lit);
+            if (valid && !(lane & 7u)) {
+                const uint32_t have = min(8u, cnt - lane);
+                const uint32_t bits = __brev((lm >> lane) & 0xFFu) >> 24;        // symbol t -> bit 7 - t
+                ring_put(q - 2u, bits | ((1u << (8u - have)) - 1u));
+            }
+        }
+        __syncwarp();
+        th += cnt; nt -= cnt;
+        const uint32_t end = Bj + ((cnt + 7u) >> 3) + ((cnt + 1u) >> 1) + total;  // behind the last payload
+        if (cnt == 32u) {
+            Bj = end;
+            flush_to(end + oal, false);
+        }
+        return end;
+    }
+
+    // End of block: emit what is queued, then the padding rules of tsq_encode.cpp:176-188.
+    // Returns the stream size; `flags` as Emitter::finish.
+    __device__ uint32_t finish(uint32_t& flags)
+    {
+        if (nt >= 32u) emit(32u);
+        const uint32_t cnt = nt;                                                 // < 32
+        const uint32_t jend = cnt ? emit(cnt) : Bj;                               // cnt == 0: Bj is where the next control byte goes
+        const uint32_t r8 = n & 7u;
+        uint32_t out_size, keep = 0;                                             // keep: trailing bytes left as pre-filled
+        flags = 0;
+        auto stale = [&](uint32_t a, uint32_t& val) -> bool {
+            if (a - lit_js < 16u) { val = in[lit_src + (a - lit_js)]; return true; }
+            return false;
+        };
+        uint32_t val;
+        if (r8 == 0) {
+            // a fresh control byte and a fresh size byte were allocated and never written
+            out_size = jend + 2u;
+            const bool s0 = stale(jend, val);
+            if (s0) { if (lane == 0) ring_put(jend + oal, val); } else flags |= kTailCtlPrefill;
+            const bool s1 = stale(jend + 1u, val);
+            if (s1) { if (lane == 0) ring_put(jend + 1u + oal, val); } else flags |= kTailNibPrefill;
+            keep = s1 ? 0u : (s0 ? 1u : 2u);
+        } else if ((n & 1u) == 0) {
+            // a fresh size byte: the reference shifts whatever it held (:183-186)
+            out_size = jend + 1u;
+            if (stale(jend, val)) { if (lane == 0) ring_put(jend + oal, val << 4); }
+            else { flags |= kTailNibShifted; keep = 1u; }
+        } else {
+            out_size = jend;
+        }
+        __syncwarp();
+        flush_to(out_size - keep + oal, true);
+        if ((flags & kTailNibShifted) && lane == 0) {                             // byte = (pre-fill << 4)
+            uint8_t* p = o_al + oal + jend;
+            *p = (uint8_t)(*p << 4);
+        }
+        return out_size;
+    }
+};
+
+__device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8_t* __restrict__ in, const uint32_t size,
+                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags)
+{
+    BlockEncoder e;
+    e.in = in; e.size = size; e.lane = lane;
+    e.oal = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
+    e.o_al = out - e.oal;
+    e.obase = smem_u32(ws.oring); e.tbase = smem_u32(ws.tok);
+    e.n = 0; e.rep = 0; e.th = 0; e.nt = 0;
+    e.Bj = 3; e.F = e.oal; e.lit_js = 0x80000000u; e.lit_src = 0;
+    if (lane < 3) e.ring_put(lane + e.oal, size >> (8u * lane));              // tsq_encode.cpp:53-55
+    __syncwarp();
+
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t i = 0, lit_from = 0;
+    uint32_t base = 1;                // first probe is position 1 (:70-72)
+    bool chain_pending = false;       // lane 0 of the next window is a post-match probe (:162-170)
+
+    for (;;) {                                                         // one window per iteration
+        // ---------------- window precompute (parallel over 32 positions)
+        const uint32_t x = base + lane;
+        uint32_t own[4], cb[4];
+        ldg16(in + x, own);
+        const uint32_t w = own[0];
+        const uint32_t h = hash17(w);
+        const uint32_t s = table[h];
+        const uint32_t M = __match_any_sync(FULL, h);
+        const uint32_t tab_cand = expand_pos(s, x);
+        ldg16(in + tab_cand, cb);
+        const uint32_t m_tab = prefix16(own, cb);                      // >= 4  <=>  the 4-byte words are equal (:100)
+        const bool anydup = __any_sync(FULL, M != (1u << lane));
+        uint32_t inP = 0, c = 0;
+        bool done = false;
+
+        while (c < 32u) {
+            if (e.nt >= 32u) e.emit(32u);                              // a full batch of tokens is waiting
+            // ------------ effective candidate of every lane given the lanes in P
+            uint32_t cand = tab_cand;
+            uint32_t m = m_tab;
+            bool ovr = false;                                          // candidate is a lane of this window
+            if (anydup) {
+                const uint32_t cm = M & lt & (inP | ~((1u << c) - 1u));
+                const uint32_t q = cm ? 31u - (uint32_t)__clz(cm) : lane;
+                const uint32_t wq = __shfl_sync(FULL, w, q);
+                if (cm) { cand = base + q; m = (wq == w) ? 4u : 0u; ovr = true; }   // exact length is taken on demand
+            }
+
+            uint32_t H, pos;
+            if (chain_pending) {
+                // lane c is the probe that follows a match (:162-170); i == base + c
+                chain_pending = false;
+                inP |= 1u << c;
+                pos = __shfl_sync(FULL, cand, c);
+                const bool eq = (__ballot_sync(FULL, m >= 4u) >> c) & 1u;
+                const uint32_t off = e.rep - pos;
+                if (!(i < size - 5u && eq && (off - 4u) < 0xFFFBu)) {
+                    if (!(i < size)) { done = true; break; }
+                    lit_from = i;                                      // outer loop restarts (:66-68)
+                    c++;
+                    continue;
+                }
+                H = c;
+            } else {
+                // ------------ literal scan from lane c (:70-100)
+                const uint32_t Fl = lit_from + 32u - base;             // lane of the forced flush (:80-98)
+                const uint32_t E = size - base;                        // lane with x == size
+                const uint32_t hi = min(31u, min(Fl, E));
+                const bool lanehit = m >= 4u && ((e.rep - cand - 4u) < 0xFFFBu) && lane >= c && lane <= hi && x < size;
+                const uint32_t hm = __ballot_sync(FULL, lanehit);
+                if (hm == 0) {
+                    if (E <= hi) {                                     // ran into the end of the block
+                        i = size;
+                        if (i - lit_from > 31u) e.literals(lit_from, i);
+                        if (i - lit_from > 0u) e.literals(lit_from, i);
+                        done = true;
+                        break;
+                    }
+                    inP |= lanes_from_to(c, hi);
+                    i = base + hi;
+                    if (Fl <= hi) e.literals(lit_from, i);             // 32 pending literals: rep moves, scan goes on
+                    c = hi + 1u;
+                    continue;
+                }
+                H = (uint32_t)__ffs((int)hm) - 1u;
+                inP |= lanes_from_to(c, H);
+                i = base + H;
+                if (i - lit_from > 31u) e.literals(lit_from, i);       // flush precedes the loop test (:80-100)
+                if (i - lit_from > 0u) e.literals(lit_from, i);        // :103-118
+                pos = __shfl_sync(FULL, cand, H);
+            }
+
+            // ---------------- one match attempt at i == base + H against pos (:126-160)
+            {
+                uint32_t k = __shfl_sync(FULL, m, H);                  // common prefix, capped at 16
+                if (__shfl_sync(FULL, (uint32_t)ovr, H)) {             // in-window candidate: compare now
+                    const uint32_t t = lane & 15u;
+                    const bool ne = __ldg(in + i + t) != __ldg(in + pos + t);
+                    const uint32_t nm = __ballot_sync(FULL, ne) | 0xFFFF0000u;
+                    k = (uint32_t)__ffs((int)nm) - 1u;
+                }
+                const uint32_t room = e.rep - pos;
+                if (k > room) k = room - 1u;                           // :139-141
+                if (k < 4u || !((room - 4u) < 0xFFFBu)) {              // :142-145 -> byte stays a literal
+                    lit_from = i;
+                    c = H + 1u;
+                    continue;
+                }
+                i += k;                                                // :154
+                e.match(room, k, i);                                   // :152-159 (mlen[k] = k-1, 16 -> 15)
+                if (!(i < size) && !(i < size - 5u)) { done = true; break; }      // probe would be unobservable
+                c = H + k;
+                chain_pending = true;
+            }
+        }
+        if (done) break;
+
+        // ---------------- leave the window: commit inserts (last writer per hash wins, :79)
+        {
+            const uint32_t mine = M & inP;
+            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) table[h] = (uint16_t)x;
+            __syncwarp();
+        }
+        base = chain_pending ? i : i + 1u;
+    }
+
+    return e.finish(flags);
+}
+
+__global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
+{
+    __shared__ WarpWs ws_all[kWarps];
+    const unsigned lane = threadIdx.x & 31u;
+    const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (slot >= a.n_slots) return;
+    WarpWs& ws = ws_all[threadIdx.x >> 5];
+    uint16_t* table = a.tables + (size_t)slot * kHashSlots;
+    for (uint64_t b = slot; b < a.nb; b += a.n_slots) {
+        uint4* t4 = reinterpret_cast<uint4*>(table);                   // tsqInit (tsq_context.cpp:77-80)
+        for (uint32_t q = lane; q < kTableBytes / 16u; q += 32u) t4[q] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        const uint64_t at = b * (uint64_t)a.block;
+        const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
+        uint32_t flags;
+        const uint32_t c = encode_block_batch(table, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
+        if (lane == 0) { a.sizes[b] = c; if (a.tailflags) a.tailflags[b] = flags; }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_encode_batch(const EncodeArgs& a, cudaStream_t st)
+{
+    if (a.nb == 0) return cudaSuccess;
+    const unsigned ctas = (a.n_slots + kWarps - 1) / kWarps;
+    encode_batch_kernel<<<ctas, kWarps * 32, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace tsqb
