@@ -261,6 +261,29 @@ def run_ours(args):
     e2e_s = float(te[0])
     e2e_value = total_all / e2e_s / 1e9
 
+    # ---- N > 1: the one exchange step of the path -- every rank frames its streams as a TSQ1 body on
+    # its GPU, then the bodies are gathered into ONE container on rank 0 (NCCL over NVLink).  Reported
+    # next to `value`, never inside it (the root's NVLink ingress bounds it).
+    gather = None
+    if world > 1:
+        from turbosqueeze_b200 import sharding as S
+        def gather_step():
+            cont, n = ctx.pack_container(slots, sizes, block, total)
+            clen_local = int(n.item())
+            return S.gather_container(cont[:clen_local], total_all, nb * world, dst=0)
+        gather_step()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        gathered = gather_step()
+        g1.record()
+        barrier()
+        tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            gather = {"ms": round(float(tg[0]), 3), "container_bytes": int(gathered.numel()),
+                      "what": "tsqb_pack_container per rank + all_gather of byte counts + variable-length gather to rank 0 (NCCL)"}
+
     if rank == 0:
         r = comp_all / total_all
         enc_gbs = total_all / (ms_enc * 1e-3) / 1e9
@@ -279,10 +302,10 @@ def run_ours(args):
                        "step": "encode all blocks then decode all blocks, device-resident"},
             "encode_gbs": round(enc_gbs, 3), "decode_gbs": round(dec_gbs, 3), "ms_encode": round(ms_enc, 4), "ms_decode": round(ms_dec, 4),
             "bit_exact_round_trip": ok,
-            "roofline": {"kernel": "encode_warp_kernel", "bound": "hbm", "achieved": round(enc_ach, 2), "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"kernel": "encode_batch_kernel", "bound": "hbm", "achieved": round(enc_ach, 2), "peak": hbm_peak, "unit": "GB/s",
                          "frac": round(enc_ach / hbm_peak, 5), "traffic": args.traffic_encode, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg), "share_of_step": round(ms_enc / (ms_enc + ms_dec), 4)},
-            "roofline_decode": {"kernel": "decode_kernel", "bound": "hbm", "achieved": round(dec_ach, 2), "peak": hbm_peak, "unit": "GB/s",
+            "roofline_decode": {"kernel": "decode_split_kernel", "bound": "hbm", "achieved": round(dec_ach, 2), "peak": hbm_peak, "unit": "GB/s",
                                 "frac": round(dec_ach / hbm_peak, 5), "traffic": args.traffic_decode,
                                 "algorithmic_bytes_per_launch": int(alg), "share_of_step": round(ms_dec / (ms_enc + ms_dec), 4)},
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": int(total + clen), "d2h_bytes_per_step": int(clen + total),
@@ -290,6 +313,9 @@ def run_ours(args):
                     "ms_per_step": round(e2e_s * 1e3, 3)},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": round(t_wall, 3),
         }
+        if gather is not None:
+            gather["encode_with_gather_gbs"] = round(total_all / ((ms_enc + gather["ms"]) * 1e-3) / 1e9, 3)
+            line["gather"] = gather
         if world == 1 and not args.no_cpu:
             codec, ckind = cpu_codec()
             threads = (os.cpu_count() or 1) if ckind == "reference" else 1
