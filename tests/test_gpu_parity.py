@@ -234,6 +234,31 @@ def test_container_pack_index_and_buffer_api(torch, ctx, oracle):
         assert T.tsq_decompress_mt(ref.compress_mt(buf[:n], 1)) == buf[:n].tobytes()   # and we read its
 
 
+def test_pipelined_host_path_equals_one_shot(torch, ctx):
+    """The chunked, stream-overlapped host path (H2D | kernels | D2H) must produce the very same container
+    as one-shot staging, including the bytes a chunk's last block reads from the next chunk."""
+    ctx.set_option("pipeline_min", 1 << 20)
+    try:
+        for kind, n, block in [("text", (5 << 20) + 4321, 65536), ("text", (3 << 20), 4096), ("rep8", (6 << 20) + 1, 1 << 20),
+                               ("random", (2 << 20) + 99, 262144)]:
+            buf = W.fill(kind, n, seed=31)
+            ctx.set_option("pipeline", 0)
+            one = ctx.compress_buffer(buf[:n], block, 0)
+            ctx.set_option("pipeline", 1)
+            piped = ctx.compress_buffer(buf[:n], block, 0)
+            if piped != one:
+                a, b = np.frombuffer(one, np.uint8), np.frombuffer(piped, np.uint8)
+                m = min(a.size, b.size)
+                bad = np.flatnonzero(a[:m] != b[:m])
+                raise AssertionError((kind, n, block, a.size, b.size, bad[:8].tolist()))
+            assert ctx.decompress_buffer(piped) == buf[:n].tobytes(), (kind, n, block)
+            ctx.set_option("pipeline", 0)
+            assert ctx.decompress_buffer(piped) == buf[:n].tobytes()
+    finally:
+        ctx.set_option("pipeline", 1)
+        ctx.set_option("pipeline_min", 64 << 20)
+
+
 @pytest.mark.parametrize("kind,block", [("text", 262144), ("random", 262144), ("rep8", 1 << 20), ("text", 4096)])
 def test_large_buffers_bit_exact_and_round_trip(torch, ctx, checker, kind, block):
     """BASELINE.json shapes at a size the multi-threaded reference finishes in seconds (256 MiB):

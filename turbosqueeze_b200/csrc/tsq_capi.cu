@@ -76,6 +76,13 @@ struct tsqb_context {
     // staging for the host-buffer entry points
     DevBuf in, slots, sizes, out, osizes, cont, offs, ext, misc;
     cudaStream_t stream = nullptr;
+    // pipelined host path: copy-in / copy-out streams, one compute stream + events per chunk in flight
+    static constexpr int kPipe = 4;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_chunk[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
+    uint64_t* h_len = nullptr;                 // pinned: per-chunk container length
+    int pipeline = 1;                          // 0: one-shot staging (round-1 v1 behaviour)
+    uint64_t pipeline_min = 64ull << 20;       // buffers below this many bytes are staged in one shot
     std::mutex mtx;
 };
 
@@ -92,9 +99,18 @@ extern "C" int tsqb_create(tsqb_context** out, int device)
     tsqb_context* c = new tsqb_context();
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaMallocHost((void**)&c->h_len, sizeof(uint64_t) * tsqb_context::kPipe) == cudaSuccess;
+    for (int k = 0; ok && k < tsqb_context::kPipe; k++)
+        ok = cudaStreamCreateWithFlags(&c->s_chunk[k], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&c->ev_done[k], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
         delete c;
-        return fail("tsqb_create: cudaStreamCreate failed");
+        return fail("tsqb_create: cannot create CUDA streams / events");
     }
     *out = c;
     g_err.clear();
@@ -109,6 +125,14 @@ extern "C" void tsqb_destroy(tsqb_context* c)
     for (DevBuf* b : {&c->tables, &c->in, &c->slots, &c->sizes, &c->out, &c->osizes, &c->cont, &c->offs, &c->ext, &c->misc})
         b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->s_in) cudaStreamDestroy(c->s_in);
+    if (c->s_out) cudaStreamDestroy(c->s_out);
+    for (int k = 0; k < tsqb_context::kPipe; k++) {
+        if (c->s_chunk[k]) cudaStreamDestroy(c->s_chunk[k]);
+        if (c->ev_in[k]) cudaEventDestroy(c->ev_in[k]);
+        if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
+    }
+    if (c->h_len) cudaFreeHost(c->h_len);
     delete c;
 }
 
@@ -124,6 +148,8 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
     if (!strcmp(key, "encode_impl"))  { c->encode_impl = (int)v; return 0; }
     if (!strcmp(key, "decode_lanes")) { c->decode_lanes = (int)v; return 0; }
     if (!strcmp(key, "encode_slots")) { c->encode_slots = v; return 0; }
+    if (!strcmp(key, "pipeline")) { c->pipeline = (int)v; return 0; }
+    if (!strcmp(key, "pipeline_min")) { c->pipeline_min = (uint64_t)v; return 0; }
     if (!strcmp(key, "l2_fetch")) {                                  // 32 / 64 / 128: DRAM fetch granularity hint
         cudaSetDevice(c->device);
         return cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) == cudaSuccess ? 0 : 1;
@@ -132,8 +158,10 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
 }
 
 // ------------------------------------------------------------------------------ layer 1: device path
+// `tables` (optional): caller-provided region of encode_slots_for(...) tables, for launches that overlap in time
 static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t total, uint32_t block, uint8_t* d_slots,
-                              uint64_t stride, uint32_t* d_sizes, uint32_t* d_tailflags, uint32_t with_ext, void* stream)
+                              uint64_t stride, uint32_t* d_sizes, uint32_t* d_tailflags, uint32_t with_ext, void* stream,
+                              uint16_t* tables = nullptr)
 {
     if (!c) return fail("tsqb_encode_blocks: null context");
     if (block == 0 || block > kBlockMax) return fail("tsqb_encode_blocks: block size %u not in 1..%u", block, kBlockMax);
@@ -146,8 +174,11 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
     const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
-    if (c->tables.ensure((size_t)a.n_slots * kTableBytes)) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
-    a.tables = (uint16_t*)c->tables.p;
+    if (tables) a.tables = tables;
+    else {
+        if (c->tables.ensure((size_t)a.n_slots * kTableBytes)) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
+        a.tables = (uint16_t*)c->tables.p;
+    }
     CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
     g_launches += 1;
     return 0;
@@ -220,6 +251,7 @@ extern "C" int tsqb_encode_host(tsqb_context* c, const uint8_t* in, uint64_t tot
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
     if (stage_input(c, in, total, nullptr, 0)) return 1;
     if (c->slots.ensure(nb * stride) || c->sizes.ensure(nb * 4)) return fail("tsqb_encode_host: out of device memory");
+    CU(cudaMemsetAsync(c->slots.p, 0, nb * stride, c->stream));          // zero-filled slots (parity contract)
     if (tsqb_encode_blocks(c, (uint8_t*)c->in.p, total, block, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, with_ext, c->stream)) return 1;
     CU(cudaMemcpyAsync(sizes, c->sizes.p, nb * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -267,6 +299,8 @@ static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, c
     const uint64_t cap = 16 + nb * (stride + 3);
     if (c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) || c->cont.ensure(cap + 256) || c->misc.ensure(64))
         return fail("compress: out of device memory");
+    // parity contract: every block's output slot is zero-filled before it is encoded
+    if (nb) CU(cudaMemsetAsync(c->slots.p, 0, nb * stride, c->stream));
     if (nb && tsqb_encode_blocks(c, (uint8_t*)c->in.p, total, block, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, with_ext, c->stream)) return 1;
     if (tsqb_pack_container(c, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, nb, total, with_ext, (uint8_t*)c->cont.p,
                             (uint64_t*)c->misc.p, c->stream)) return 1;
@@ -287,6 +321,145 @@ static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, c
     return 0;
 }
 
+// ------------------------------------------------------------------------------ pipelined host path
+// The host entry points move 2 x (U + C) bytes over PCIe around ~40 ms of kernels.  Above kPipeMin
+// bytes the input is cut into up to kPipe chunks of whole blocks: chunk k's H2D copy, its kernels and
+// the D2H copy of its result run on different streams, so the copies of one chunk hide behind the
+// kernels of another (this is what the reference's reader / worker / writer threads do on the CPU,
+// tsq_threads.cpp:52-275).  The chunks' kernels overlap in time, which keeps thousands of blocks in
+// flight; every chunk therefore gets its own hash-table region.
+
+static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
+                              uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size)
+{
+    constexpr int K = tsqb_context::kPipe;
+    const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
+    const uint64_t per = (nb + K - 1) / K;                                   // blocks per chunk
+    const int nchunks = (int)((nb + per - 1) / per);
+    const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
+    uint64_t slots_tab[K], tab_at[K], tab_total = 0;
+    for (int k = 0; k < nchunks; k++) {
+        const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
+        slots_tab[k] = encode_slots_for(impl, b1 - b0, c->sm_count, c->encode_slots);
+        tab_at[k] = tab_total; tab_total += slots_tab[k];
+    }
+    const uint64_t ccap = 16 + per * (stride + 3) + 256;                     // container capacity of one chunk
+    if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
+        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || c->tables.ensure(tab_total * kTableBytes))
+        return fail("compress: out of device memory");
+    uint8_t* d_in = (uint8_t*)c->in.p;
+    CU(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
+    if (tail && tail_n) CU(cudaMemcpyAsync(d_in + total, tail, tail_n, cudaMemcpyHostToDevice, c->s_in));
+    for (int k = 0; k < nchunks; k++) {
+        const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
+        const uint64_t lo = b0 * block, hi = (b1 * block < total) ? b1 * block : total;
+        // the last block of the chunk reads a few bytes past it (tsq_encode.cpp:74,126-128): ship them with this chunk
+        const uint64_t hi_tail = (hi + TSQB_INPUT_PAD < total) ? hi + TSQB_INPUT_PAD : total;
+        CU(cudaMemcpyAsync(d_in + lo, in + lo, hi_tail - lo, cudaMemcpyHostToDevice, c->s_in));
+        CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        cudaStream_t st = c->s_chunk[k];
+        CU(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+        CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
+        // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
+        if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
+                               with_ext, st, (uint16_t*)c->tables.p + tab_at[k] * kHashSlots)) return 1;
+        uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
+        uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
+        CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,
+                       (uint64_t*)c->offs.p + b0 + k, st));
+        g_launches += 2;
+        CU(cudaMemcpyAsync(&c->h_len[k], d_len, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(c->ev_done[k], st));
+    }
+    // results leave in order; the body of chunk k goes behind the bodies before it
+    uint8_t* host = host_out;
+    uint64_t at = 16;
+    for (int k = 0; k < nchunks; k++) {
+        CU(cudaEventSynchronize(c->ev_done[k]));
+        const uint64_t body = c->h_len[k] - 16;
+        if (!host) {                                                          // malloc mode: size known only now -> worst case
+            host = (uint8_t*)malloc(16 + nb * (stride + 3));
+            if (!host) return fail("compress: malloc failed");
+        } else if (host_out && at + body > host_cap) {
+            return fail("compress: output needs more than the %llu bytes the caller gave", (unsigned long long)host_cap);
+        }
+        CU(cudaMemcpyAsync(host + at, (uint8_t*)c->cont.p + (uint64_t)k * ccap + 16, body, cudaMemcpyDeviceToHost, c->s_out));
+        at += body;
+    }
+    CU(cudaStreamSynchronize(c->s_out));
+    memcpy(host, "TSQ1", 4);                                                  // turbosqueeze.cpp:64-67
+    const uint32_t nb32 = (uint32_t)nb;
+    memcpy(host + 4, &nb32, 4);
+    memcpy(host + 8, &total, 8);
+    if (out) *out = host;
+    *out_size = at;
+    return 0;
+}
+
+// Container in host memory: the u24 chain is walked on the host (it is serial by construction,
+// tsq_threads.cpp:480-484, and the bytes are right here), then chunks of blocks are copied, decoded and
+// copied back on separate streams.  Returns 1 with g_err set on failure, -1 when the container is not
+// regular (mixed block sizes / flags): the caller then falls back to the one-shot path.
+static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* host_out, uint64_t host_cap,
+                                uint8_t** out, uint64_t* out_size)
+{
+    constexpr int K = tsqb_context::kPipe;
+    std::vector<uint64_t> offs;
+    std::vector<uint32_t> sizes;
+    uint32_t with_ext = 0, block = 0;
+    uint64_t total = 0;
+    uint32_t nb_hdr;
+    memcpy(&nb_hdr, in + 4, 4);                                               // tsq_threads.cpp:728-757 reads this many blocks
+    for (uint64_t at = 16; at + 3 <= in_size && offs.size() < nb_hdr;) {
+        uint32_t len = (uint32_t)in[at] | ((uint32_t)in[at + 1] << 8) | ((uint32_t)in[at + 2] << 16);
+        const uint32_t ext = len >> 23;
+        len &= 0x7FFFFFu;
+        if (len < 3 || at + 3 + len > in_size) break;                         // turbosqueeze.cpp:119-136: stop at a short read
+        const uint8_t* h = in + at + 3;
+        const uint32_t u = (uint32_t)h[0] | ((uint32_t)h[1] << 8) | ((uint32_t)h[2] << 16);
+        if (offs.empty()) { with_ext = ext; block = u; }
+        else if (ext != with_ext) return -1;
+        if (u > kBlockMax || u > block || (total % (block ? block : 1)) != 0) return -1;   // only the last block may be short
+        offs.push_back(at + 3); sizes.push_back(len);
+        total += u;
+        at += 3 + (uint64_t)len;
+    }
+    const uint64_t nb = offs.size();
+    if (nb == 0 || block == 0) return -1;
+    uint8_t* host = host_out;
+    if (!host) {
+        host = (uint8_t*)malloc(total + 128);                                 // tsq_threads.cpp:795 allocates outsize+128
+        if (!host) return fail("decompress: malloc failed");
+    } else if (total > host_cap) {
+        return fail("decompress: output needs %llu bytes, caller gave %llu", (unsigned long long)total, (unsigned long long)host_cap);
+    }
+    if (c->cont.ensure(in_size + 512) || c->offs.ensure(nb * 8) || c->sizes.ensure(nb * 4) || c->osizes.ensure(nb * 4) ||
+        c->out.ensure(nb * (uint64_t)block))
+        return fail("decompress: out of device memory");
+    CU(cudaMemcpyAsync(c->offs.p, offs.data(), nb * 8, cudaMemcpyHostToDevice, c->s_in));
+    CU(cudaMemcpyAsync(c->sizes.p, sizes.data(), nb * 4, cudaMemcpyHostToDevice, c->s_in));
+    const uint64_t per = (nb + K - 1) / K;
+    const int nchunks = (int)((nb + per - 1) / per);
+    for (int k = 0; k < nchunks; k++) {
+        const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
+        const uint64_t lo = offs[b0], hi = offs[b1 - 1] + sizes[b1 - 1];
+        CU(cudaMemcpyAsync((uint8_t*)c->cont.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->s_in));
+        CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        cudaStream_t st = c->s_chunk[k];
+        CU(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+        if (tsqb_decode_blocks(c, (uint8_t*)c->cont.p, (uint64_t*)c->offs.p + b0, 0, (uint32_t*)c->sizes.p + b0, b1 - b0,
+                               (uint8_t*)c->out.p + b0 * (uint64_t)block, block, (uint32_t*)c->osizes.p + b0, with_ext, st)) return 1;
+        CU(cudaEventRecord(c->ev_done[k], st));
+        CU(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
+        const uint64_t olo = b0 * (uint64_t)block, ohi = (b1 * (uint64_t)block < total) ? b1 * (uint64_t)block : total;
+        CU(cudaMemcpyAsync(host + olo, (uint8_t*)c->out.p + olo, ohi - olo, cudaMemcpyDeviceToHost, c->s_out));
+    }
+    CU(cudaStreamSynchronize(c->s_out));
+    if (out) *out = host;
+    *out_size = total;
+    return 0;
+}
+
 extern "C" int tsqb_compress_buffer(tsqb_context* c, const uint8_t* in, uint64_t total, uint32_t block, uint32_t with_ext,
                                     uint8_t** out, uint64_t* out_size)
 {
@@ -294,6 +467,7 @@ extern "C" int tsqb_compress_buffer(tsqb_context* c, const uint8_t* in, uint64_t
     if (block == 0 || block > kBlockMax) return fail("tsqb_compress_buffer: bad block size %u", block);
     std::lock_guard<std::mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
+    if (c->pipeline && total >= c->pipeline_min) return compress_pipelined(c, in, total, nullptr, 0, block, with_ext, nullptr, 0, out, out_size);
     return compress_locked(c, in, total, nullptr, 0, block, with_ext, nullptr, 0, out, out_size);
 }
 
@@ -304,6 +478,7 @@ extern "C" int tsqb_compress_into(tsqb_context* c, const uint8_t* in, uint64_t t
     if (block == 0 || block > kBlockMax) return fail("tsqb_compress_into: bad block size %u", block);
     std::lock_guard<std::mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
+    if (c->pipeline && total >= c->pipeline_min) return compress_pipelined(c, in, total, nullptr, 0, block, with_ext, out, out_capacity, nullptr, out_size);
     return compress_locked(c, in, total, nullptr, 0, block, with_ext, out, out_capacity, nullptr, out_size);
 }
 
@@ -381,6 +556,10 @@ extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64
     if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_buffer: not a TSQ1 container");
     std::lock_guard<std::mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
+    if (c->pipeline && in_size >= c->pipeline_min) {
+        const int r = decompress_pipelined(c, in, in_size, nullptr, 0, out, out_size);
+        if (r >= 0) return r;
+    }
     return decompress_locked(c, in, in_size, nullptr, 0, out, out_size);
 }
 
@@ -391,6 +570,10 @@ extern "C" int tsqb_decompress_into(tsqb_context* c, const uint8_t* in, uint64_t
     if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_into: not a TSQ1 container");
     std::lock_guard<std::mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
+    if (c->pipeline && in_size >= c->pipeline_min) {
+        const int r = decompress_pipelined(c, in, in_size, out, out_capacity, nullptr, out_size);
+        if (r >= 0) return r;
+    }
     return decompress_locked(c, in, in_size, out, out_capacity, nullptr, out_size);
 }
 
