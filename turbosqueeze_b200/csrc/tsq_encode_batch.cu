@@ -322,8 +322,46 @@ __device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8
         uint32_t inP = 0, c = 0;
         bool done = false;
 
+        // A lane is a SIMPLE hit when its probe succeeds and yields the match (pos = tab_cand, k = m_tab)
+        // whatever the parse did before it: the open pair started at most 16 bytes earlier (rep in
+        // [x - 16, x]), so with D = x - tab_cand in [32, 0xFFFE] the offset test (:100,:144-145,:170) holds
+        // and the source cannot reach the pair start (:139-141); x + 16 < size - 5 keeps the end-of-block
+        // conditions (:170-172) out of the picture.  Windows with two equal hashes are left to the general path.
+        const uint32_t D = x - tab_cand;
+        const bool simple = !anydup && m_tab >= 4u && D >= 32u && D <= 0xFFFEu && size > 21u && x + 16u < size - 5u;
+        const uint32_t simple_mask = __ballot_sync(FULL, simple);
+        const uint32_t nxt = lane + m_tab;                             // lane of the probe that follows this lane's match
+
         while (c < 32u) {
             if (e.nt >= 32u) e.emit(32u);                              // a full batch of tokens is waiting
+
+            // ------------ fast path: a chain of simple matches starting at the post-match probe of lane c.
+            // One shuffle per match finds the chain; its tokens are then built by the matched lanes in parallel.
+            if (chain_pending && ((simple_mask >> c) & 1u)) {
+                uint32_t V = 0, cur = c;
+                do {
+                    V |= 1u << cur;
+                    cur = __shfl_sync(FULL, nxt, cur);
+                } while (cur < 32u && ((simple_mask >> cur) & 1u));
+                const uint32_t below = V & lt;
+                const uint32_t rank = (uint32_t)__popc(below), cnt = (uint32_t)__popc(V);
+                const uint32_t pred = below ? 31u - (uint32_t)__clz(below) : lane;
+                const uint32_t x_pred = __shfl_sync(FULL, x, pred);
+                const uint32_t last = 31u - (uint32_t)__clz(V);
+                // pair start seen by this lane's symbol (rep_last_i): its own start when it opens a pair, else
+                // the start of the symbol before it (:159: rep moves when the symbol count becomes even)
+                const uint32_t r = (((e.n + rank) & 1u) == 0) ? x : (below ? x_pred : e.rep);
+                if ((V >> lane) & 1u)
+                    asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(e.tbase + (((e.th + e.nt + rank) & (kTok - 1)) << 2)),
+                                 "r"(((m_tab - 1u) << 27) | (r - tab_cand)) : "memory");
+                inP |= V;
+                e.nt += cnt;
+                e.n += cnt;
+                i = base + cur;                                        // cur = last + k(last): position after the chain
+                e.rep = (e.n & 1u) ? base + last : i;
+                c = cur;                                               // the next probe is again a post-match probe
+                continue;
+            }
             // ------------ effective candidate of every lane given the lanes in P
             uint32_t cand = tab_cand;
             uint32_t m = m_tab;
@@ -376,6 +414,7 @@ __device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8
                 i = base + H;
                 if (i - lit_from > 31u) e.literals(lit_from, i);       // flush precedes the loop test (:80-100)
                 if (i - lit_from > 0u) e.literals(lit_from, i);        // :103-118
+                if ((simple_mask >> H) & 1u) { c = H; chain_pending = true; continue; }   // same outcome as a post-match probe
                 pos = __shfl_sync(FULL, cand, H);
             }
 
