@@ -22,9 +22,9 @@
 //     symbol s lands on bytes owned by later symbols, and those write their own byte later in
 //     program order, so no per-byte predicate is needed (the reference uses the same blind copy,
 //     tsq_decode.cpp:74-85, serially);
-//   * symbols whose source lies inside the output of the same step wait for it in follow-up rounds
-//     (sources always precede their own pair, tsq_encode.cpp:139-141, so every round releases at
-//     least the first pending pair);
+//   * symbols whose source lies inside the output of the same step are copied afterwards, in position
+//     order, lane-per-byte with their exact length (sources always precede their own pair,
+//     tsq_encode.cpp:139-141, so everything such a symbol reads is in place when it is reached);
 //   * after the step, all complete 16-byte units of the output ring are written to HBM with
 //     coalesced 128-bit stores.  Nothing is ever written past the block's decoded size.
 #include "tsq_device.cuh"
@@ -373,7 +373,17 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
 
         // complete 16-byte units of the ring -> HBM, one 128-bit load/store per lane
         auto flush_units = [&](uint32_t E) {                                     // E 16-byte aligned, F 16-byte aligned
-            for (uint32_t at = F + 16u * lane; at < E; at += 512u) {
+            // a step leaves at most 33 units behind: two predicated 128-bit moves per lane cover it
+#pragma unroll
+            for (int rep = 0; rep < 2; rep++) {
+                const uint32_t at = F + 16u * lane + 512u * rep;
+                if (at < E) {
+                    uint4 x;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
+                    *reinterpret_cast<uint4*>(o_al + at) = x;
+                }
+            }
+            for (uint32_t at = F + 16u * lane + 1024u; at < E; at += 512u) {     // never taken for regular steps
                 uint4 x;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
                 *reinterpret_cast<uint4*>(o_al + at) = x;
@@ -466,25 +476,21 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 const bool owrap = __any_sync(FULL, active && ((q & kOMask) + 16u > OUT_RING));
                 __syncwarp();                                                    // reconverge before the ordered stores
                 if (placed) store16_desc(obase, kOMask, q, v, owrap);
-                // ---- follow-up rounds: sources inside this step's output.  Every round re-stores ALL placed
-                // symbols in the same descending order, which repairs the garbage tails the newly placed ones
-                // throw onto symbols after them.
+                // ---- symbols whose source lies inside this step's output: in position order, one at a time, the
+                // warp copying a symbol's bytes lane-per-byte with exact length (no garbage tail, so nothing placed
+                // before has to be repaired).  Sources always precede their own pair (tsq_encode.cpp:139-141), so by
+                // the time a symbol is reached everything it reads is in place.
                 uint32_t pm = __ballot_sync(FULL, pending);
                 while (pm) {
-                    __syncwarp();                                                // stores above are visible to the warp
-                    // every pending symbol whose source ends before the first pending pair is now safe; that
-                    // pair itself is always released (its sources precede its own start in every valid
-                    // stream; releasing it unconditionally also bounds the loop on corrupt input)
-                    const uint32_t firstlane = (uint32_t)__ffs((int)pm) - 1u;
-                    const uint32_t frontier = __shfl_sync(FULL, q, firstlane & ~1u);   // even lane's q == start of that pair
-                    now = pending && (srcq + len <= frontier || (lane >> 1) == (firstlane >> 1));
-                    pending = pending && !now;
-                    const bool wrap = __any_sync(FULL, now && ((srcq & kOMask) + 20u > OUT_RING));
-                    if (now) load16_smem(obase, kOMask, srcq, v, wrap);
-                    placed = placed || now;
-                    __syncwarp();
-                    if (placed) store16_desc(obase, kOMask, q, v, owrap);
-                    pm = __ballot_sync(FULL, pending);
+                    __syncwarp();                                                // stores so far are visible to the warp
+                    const uint32_t pl = (uint32_t)__ffs((int)pm) - 1u;
+                    const uint32_t s_q = __shfl_sync(FULL, q, pl), s_src = __shfl_sync(FULL, srcq, pl), s_len = __shfl_sync(FULL, len, pl);
+                    if (lane < s_len) {
+                        uint32_t byte;
+                        asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + lane) & kOMask)) : "memory");
+                        asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + lane) & kOMask)), "r"(byte) : "memory");
+                    }
+                    pm &= pm - 1u;
                 }
                 __syncwarp();
                 if (F & 15u) flush(J1, false); else if ((J1 & ~15u) > F) flush_units(J1 & ~15u);
