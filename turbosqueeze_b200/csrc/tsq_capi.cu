@@ -176,7 +176,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
     if (tables) a.tables = tables;
     else {
-        if (c->tables.ensure((size_t)a.n_slots * kTableBytes)) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
+        if (c->tables.ensure((size_t)a.n_slots * encode_table_bytes(impl))) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
         a.tables = (uint16_t*)c->tables.p;
     }
     CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
@@ -345,7 +345,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     }
     const uint64_t ccap = 16 + per * (stride + 3) + 256;                     // container capacity of one chunk
     if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
-        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || c->tables.ensure(tab_total * kTableBytes))
+        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || c->tables.ensure(tab_total * encode_table_bytes(impl)))
         return fail("compress: out of device memory");
     uint8_t* d_in = (uint8_t*)c->in.p;
     CU(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
@@ -362,7 +362,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
         CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
         // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
         if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
-                               with_ext, st, (uint16_t*)c->tables.p + tab_at[k] * kHashSlots)) return 1;
+                               with_ext, st, (uint16_t*)((uint8_t*)c->tables.p + tab_at[k] * encode_table_bytes(impl)))) return 1;
         uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
         uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
         CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,

@@ -21,6 +21,8 @@ uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_over
     return (uint32_t)slots;
 }
 
+uint32_t encode_table_bytes(int impl) { return impl == 3 ? kFatTableBytes : kTableBytes; }
+
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int /*sm_count*/, cudaStream_t st)
 {
     if (impl == 1 || ext) return launch_encode_scalar(a, ext, st);

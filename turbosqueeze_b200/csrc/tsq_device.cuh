@@ -9,6 +9,7 @@ constexpr uint32_t kBlockMax   = 1u << 22;          // TSQ_BLOCK_SZ   (reference
 constexpr uint32_t kHashSlots  = 1u << 17;          // 2^TSQ_HASH_BITS (reference turbosqueeze.h:41)
 constexpr uint32_t kHashMask   = kHashSlots - 1u;
 constexpr uint32_t kTableBytes = kHashSlots * 2u;   // TSQ_HASH_SZ
+constexpr uint32_t kFatTableBytes = kHashSlots * 8u;   // 64-bit entries of the batch encoder (tsq_encode_batch.cu)
 
 struct EncodeArgs {
     const uint8_t* in;        // contiguous input, `total` bytes + >= 128 readable
@@ -37,6 +38,8 @@ struct DecodeArgs {
 // encode_impl: 1 = scalar (one thread per block), 2 = warp per block (byte-at-a-time emitter),
 // 3 = warp per block with token batches (tsq_encode_batch.cu, the default without extensions).
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int sm_count, cudaStream_t st);
+// bytes of one hash table of launch_encode(impl)
+uint32_t    encode_table_bytes(int impl);
 // how many hash tables launch_encode(impl) will use for nb blocks (caller sizes a.tables from it)
 uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);
 

@@ -85,6 +85,19 @@ __device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4
     if constexpr (T > 0) store_bytes_desc<T - 1>(ad, v, lit);
 }
 
+// Table entry of this kernel.  The reference stores the low 16 bits of the position (tsq_encode.cpp:79);
+// here an entry is 64 bits: the full position (22 bits; its low 16 bits play the reference's role, so the
+// candidate is the same), a 15-bit tag = word >> 17, and the three input bytes behind the hashed word.
+// hash = (w ^ (w >> 12)) & 0x1FFFF determines bits 0..16 of w once bits 17..31 are known (b_i = h_i ^ b_{i+12}
+// downwards), so "same slot and same tag" is EXACTLY "same 4-byte word": the hit test of :100 and match
+// lengths up to 6 need no access to the candidate's bytes, which removes most of the second DRAM access
+// per probe.  An all-zero entry is the reference's empty entry (position 0 is never inserted, :70-72).
+__device__ __forceinline__ uint2 make_entry(uint32_t pos, uint32_t w, uint32_t next4)
+{
+    const uint32_t tag = w >> 17;
+    return make_uint2(pos | (tag << 22), (tag >> 10) | (next4 << 8));
+}
+
 __device__ __forceinline__ uint32_t lanes_from_to(uint32_t lo, uint32_t hi)   // bits lo..hi inclusive
 {
     return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
@@ -247,7 +260,7 @@ struct BlockEncoder {
         return end;
     }
 
-    // End of block: emit what is queued, then the padding rules of tsq_encode.cpp:176-188.
+    // End of block, after everything queued was emitted: the padding rules of tsq_encode.cpp:176-188.
     // Returns the stream size; `flags` as Emitter::finish.
     __device__ uint32_t finish(uint32_t& flags)
     {
@@ -288,7 +301,7 @@ struct BlockEncoder {
     }
 };
 
-__device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8_t* __restrict__ in, const uint32_t size,
+__device__ uint32_t encode_block_batch(uint2* __restrict__ table, const uint8_t* __restrict__ in, const uint32_t size,
                                        uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags)
 {
     BlockEncoder e;
@@ -313,11 +326,28 @@ __device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8
         ldg16(in + x, own);
         const uint32_t w = own[0];
         const uint32_t h = hash17(w);
-        const uint32_t s = table[h];
+        const uint2 ent = table[h];
         const uint32_t M = __match_any_sync(FULL, h);
-        const uint32_t tab_cand = expand_pos(s, x);
-        ldg16(in + tab_cand, cb);
-        const uint32_t m_tab = prefix16(own, cb);                      // >= 4  <=>  the 4-byte words are equal (:100)
+        // Fat entry (see make_entry): position, the 15 word bits the hash does not determine, and the 3 bytes
+        // behind the word.  An empty entry is the reference's zero entry: candidate = start of the 64 KiB
+        // segment (expand_pos(0, x)), one shared, cache-resident location.
+        const uint32_t p22 = ent.x & 0x3FFFFFu;
+        const uint32_t tab_cand = expand_pos(p22 & 0xFFFFu, x);
+        uint32_t m_tab;
+        bool need_load = true;
+        if ((ent.x | ent.y) != 0u && tab_cand == p22) {
+            // the entry really describes in[tab_cand]: same hash and same high word bits <=> same word (:100)
+            const uint32_t tag = (ent.x >> 22) | ((ent.y & 31u) << 10);
+            if (tag != (w >> 17)) { m_tab = 0; need_load = false; }
+            else {
+                const uint32_t d = ((ent.y >> 8) ^ own[1]) & 0xFFFFFFu;       // bytes 4..6 behind the word
+                if (d) { m_tab = 4u + (((uint32_t)__ffs((int)d) - 1u) >> 3); need_load = false; }
+            }
+        }
+        if (need_load) {                                               // empty / aliased entry, or a match of >= 7 bytes
+            ldg16(in + tab_cand, cb);
+            m_tab = prefix16(own, cb);                                 // >= 4  <=>  the 4-byte words are equal (:100)
+        }
         const bool anydup = __any_sync(FULL, M != (1u << lane));
         uint32_t inP = 0, c = 0;
         bool done = false;
@@ -326,14 +356,14 @@ __device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8
         // whatever the parse did before it: the open pair started at most 16 bytes earlier (rep in
         // [x - 16, x]), so with D = x - tab_cand in [32, 0xFFFE] the offset test (:100,:144-145,:170) holds
         // and the source cannot reach the pair start (:139-141); x + 16 < size - 5 keeps the end-of-block
-        // conditions (:170-172) out of the picture.  Windows with two equal hashes are left to the general path.
+        // conditions (:170-172) out of the picture.  A lane whose hash occurs twice in the window is left to the general path.
         const uint32_t D = x - tab_cand;
-        const bool simple = !anydup && m_tab >= 4u && D >= 32u && D <= 0xFFFEu && size > 21u && x + 16u < size - 5u;
+        const bool simple = M == (1u << lane) && m_tab >= 4u && D >= 32u && D <= 0xFFFEu && size > 21u && x + 16u < size - 5u;
         const uint32_t simple_mask = __ballot_sync(FULL, simple);
         const uint32_t nxt = lane + m_tab;                             // lane of the probe that follows this lane's match
 
         while (c < 32u) {
-            if (e.nt >= 32u) e.emit(32u);                              // a full batch of tokens is waiting
+            if (e.nt >= 32u) e.emit(32u);
 
             // ------------ fast path: a chain of simple matches starting at the post-match probe of lane c.
             // One shuffle per match finds the chain; its tokens are then built by the matched lanes in parallel.
@@ -446,7 +476,7 @@ __device__ uint32_t encode_block_batch(uint16_t* __restrict__ table, const uint8
         // ---------------- leave the window: commit inserts (last writer per hash wins, :79)
         {
             const uint32_t mine = M & inP;
-            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) table[h] = (uint16_t)x;
+            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) table[h] = make_entry(x, w, own[1]);
             __syncwarp();
         }
         base = chain_pending ? i : i + 1u;
@@ -462,10 +492,10 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= a.n_slots) return;
     WarpWs& ws = ws_all[threadIdx.x >> 5];
-    uint16_t* table = a.tables + (size_t)slot * kHashSlots;
+    uint2* table = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.tables) + (size_t)slot * kFatTableBytes);
     for (uint64_t b = slot; b < a.nb; b += a.n_slots) {
         uint4* t4 = reinterpret_cast<uint4*>(table);                   // tsqInit (tsq_context.cpp:77-80)
-        for (uint32_t q = lane; q < kTableBytes / 16u; q += 32u) t4[q] = make_uint4(0, 0, 0, 0);
+        for (uint32_t q = lane; q < kFatTableBytes / 16u; q += 32u) t4[q] = make_uint4(0, 0, 0, 0);
         __syncwarp();
         const uint64_t at = b * (uint64_t)a.block;
         const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
