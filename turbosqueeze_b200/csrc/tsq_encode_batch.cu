@@ -360,6 +360,12 @@ __device__ uint32_t encode_block_batch(uint2* __restrict__ table, const uint8_t*
         const uint32_t D = x - tab_cand;
         const bool simple = M == (1u << lane) && m_tab >= 4u && D >= 32u && D <= 0xFFFEu && size > 21u && x + 16u < size - 5u;
         const uint32_t simple_mask = __ballot_sync(FULL, simple);
+        // The same for the hit that ENDS a literal scan: there the test uses the pair start from before the
+        // pending literals are flushed (:80-100), up to 16 + 31 bytes back, hence the wider margin.
+        const uint32_t simple_scan_mask = __ballot_sync(FULL, simple && D >= 64u);
+        // A lane is a CERTAIN MISS when its word differs from its candidate's and no other lane of the window
+        // can change that candidate: the probe fails whatever the parse did (and the block does not end nearby).
+        const uint32_t miss_mask = __ballot_sync(FULL, M == (1u << lane) && m_tab < 4u && size > 21u && x + 16u < size - 5u);
         const uint32_t nxt = lane + m_tab;                             // lane of the probe that follows this lane's match
 
         while (c < 32u) {
@@ -390,6 +396,30 @@ __device__ uint32_t encode_block_batch(uint2* __restrict__ table, const uint8_t*
                 i = base + cur;                                        // cur = last + k(last): position after the chain
                 e.rep = (e.n & 1u) ? base + last : i;
                 c = cur;                                               // the next probe is again a post-match probe
+                if (cur < 32u && ((miss_mask >> cur) & 1u)) {
+                    // ... and it certainly fails (:170): the byte at lane cur starts a literal run (:66-68)
+                    chain_pending = false;
+                    inP |= 1u << cur;
+                    lit_from = i;
+                    const uint32_t rest = ~miss_mask & ~((2u << cur) - 1u);    // lanes behind cur that might hit
+                    const uint32_t H2 = rest ? (uint32_t)__ffs((int)rest) - 1u : 32u;
+                    if (H2 < 32u && ((simple_scan_mask >> H2) & 1u)) {
+                        // certain misses up to H2 - 1, a certain hit at H2: the scan of :70-100 ends there.  The run
+                        // is H2 - cur <= 31 bytes, so no forced flush happens on the way (:80-98).
+                        inP |= lanes_from_to(cur + 1u, H2);
+                        i = base + H2;
+                        e.literals(lit_from, i);                       // :103-118
+                        c = H2;
+                        chain_pending = true;                          // same outcome as a post-match probe at H2
+                    } else if (H2 == 32u) {
+                        // certain misses up to the end of the window: the run continues in the next one
+                        if (cur < 31u) inP |= lanes_from_to(cur + 1u, 31u);
+                        i = base + 31u;
+                        c = 32u;
+                    } else {
+                        c = cur + 1u;                                  // an uncertain lane ahead: the general scan takes over
+                    }
+                }
                 continue;
             }
             // ------------ effective candidate of every lane given the lanes in P
