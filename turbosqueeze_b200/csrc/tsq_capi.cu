@@ -53,13 +53,15 @@ extern "C" int tsqb_device_count(void)
 struct DevBuf {
     void*  p = nullptr;
     size_t cap = 0;
+    bool zero_on_alloc = false;
     int ensure(size_t n)
     {
         if (n <= cap) return 0;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
         const size_t want = (n + (1u << 20)) & ~(size_t)((1u << 20) - 1);
-        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); return 1; }
+        if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return 1; }
+        if (zero_on_alloc && cudaMemset(p, 0, want) != cudaSuccess) { cudaGetLastError(); cudaFree(p); p = nullptr; return 1; }
         cap = want;
         return 0;
     }
@@ -72,7 +74,9 @@ struct tsqb_context {
     int encode_impl = 0;       // 0 auto, 1 scalar, 2 warp
     int decode_lanes = 0;      // 0 auto
     int64_t encode_slots = 0;  // 0 auto
-    DevBuf tables;             // hash tables of the blocks in flight
+    DevBuf tables;             // hash tables of the blocks in flight (zeroed when allocated: epoch 0 = empty)
+    DevBuf ftables;            // batch encoder: 32-byte entries, only ever written by that kernel, zeroed at allocation
+    uint64_t launch_id = 0;    // encode launches so far: the epoch of the batch encoder's table entries
     // staging for the host-buffer entry points
     DevBuf in, slots, sizes, out, osizes, cont, offs, ext, misc;
     cudaStream_t stream = nullptr;
@@ -97,6 +101,7 @@ extern "C" int tsqb_create(tsqb_context** out, int device)
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     tsqb_context* c = new tsqb_context();
+    c->ftables.zero_on_alloc = true;                                  // epoch 0 = never written
     c->device = device;
     c->sm_count = prop.multiProcessorCount;
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
@@ -122,7 +127,7 @@ extern "C" void tsqb_destroy(tsqb_context* c)
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
-    for (DevBuf* b : {&c->tables, &c->in, &c->slots, &c->sizes, &c->out, &c->osizes, &c->cont, &c->offs, &c->ext, &c->misc})
+    for (DevBuf* b : {&c->tables, &c->ftables, &c->in, &c->slots, &c->sizes, &c->out, &c->osizes, &c->cont, &c->offs, &c->ext, &c->misc})
         b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->s_in) cudaStreamDestroy(c->s_in);
@@ -172,12 +177,14 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     EncodeArgs a;
     a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
+    a.epoch = (++c->launch_id) << 20;                                 // + the slot's block counter, < 2^20
     const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
     if (tables) a.tables = tables;
     else {
-        if (c->tables.ensure((size_t)a.n_slots * encode_table_bytes(impl))) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
-        a.tables = (uint16_t*)c->tables.p;
+        DevBuf& tb = impl == 3 ? c->ftables : c->tables;
+        if (tb.ensure((size_t)a.n_slots * encode_table_bytes(impl))) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
+        a.tables = (uint16_t*)tb.p;
     }
     CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
     g_launches += 1;
@@ -345,7 +352,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     }
     const uint64_t ccap = 16 + per * (stride + 3) + 256;                     // container capacity of one chunk
     if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
-        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || c->tables.ensure(tab_total * encode_table_bytes(impl)))
+        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || (impl == 3 ? c->ftables : c->tables).ensure(tab_total * encode_table_bytes(impl)))
         return fail("compress: out of device memory");
     uint8_t* d_in = (uint8_t*)c->in.p;
     CU(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
@@ -362,7 +369,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
         CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
         // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
         if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
-                               with_ext, st, (uint16_t*)((uint8_t*)c->tables.p + tab_at[k] * encode_table_bytes(impl)))) return 1;
+                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl)))) return 1;
         uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
         uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
         CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,

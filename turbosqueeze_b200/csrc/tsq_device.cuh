@@ -9,7 +9,7 @@ constexpr uint32_t kBlockMax   = 1u << 22;          // TSQ_BLOCK_SZ   (reference
 constexpr uint32_t kHashSlots  = 1u << 17;          // 2^TSQ_HASH_BITS (reference turbosqueeze.h:41)
 constexpr uint32_t kHashMask   = kHashSlots - 1u;
 constexpr uint32_t kTableBytes = kHashSlots * 2u;   // TSQ_HASH_SZ
-constexpr uint32_t kFatTableBytes = kHashSlots * 8u;   // 64-bit entries of the batch encoder (tsq_encode_batch.cu)
+constexpr uint32_t kFatTableBytes = kHashSlots * 32u;  // one 32-byte sector per entry: batch encoder (tsq_encode_batch.cu)
 
 struct EncodeArgs {
     const uint8_t* in;        // contiguous input, `total` bytes + >= 128 readable
@@ -20,7 +20,8 @@ struct EncodeArgs {
     uint64_t       stride;
     uint32_t*      sizes;     // compressed size per block
     uint32_t*      tailflags; // optional: kTail* flags per block (see tsq_encode_common.cuh)
-    uint16_t*      tables;    // n_slots tables of kHashSlots u16
+    uint16_t*      tables;    // n_slots tables (kTableBytes each; kFatTableBytes for the batch encoder)
+    uint64_t       epoch;     // batch encoder: entries written under another epoch are empty (no per-block zeroing)
     uint32_t       n_slots;
 };
 

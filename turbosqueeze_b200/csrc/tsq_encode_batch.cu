@@ -86,16 +86,24 @@ __device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4
 }
 
 // Table entry of this kernel.  The reference stores the low 16 bits of the position (tsq_encode.cpp:79);
-// here an entry is 64 bits: the full position (22 bits; its low 16 bits play the reference's role, so the
-// candidate is the same), a 15-bit tag = word >> 17, and the three input bytes behind the hashed word.
-// hash = (w ^ (w >> 12)) & 0x1FFFF determines bits 0..16 of w once bits 17..31 are known (b_i = h_i ^ b_{i+12}
-// downwards), so "same slot and same tag" is EXACTLY "same 4-byte word": the hit test of :100 and match
-// lengths up to 6 need no access to the candidate's bytes, which removes most of the second DRAM access
-// per probe.  An all-zero entry is the reference's empty entry (position 0 is never inserted, :70-72).
-__device__ __forceinline__ uint2 make_entry(uint32_t pos, uint32_t w, uint32_t next4)
+// here an entry is one 32-byte sector:
+//   A.x  position (22 bits; its low 16 bits play the reference's role, so the candidate is the same)
+//        | low 10 bits of the tag;   A.y  high 5 bits of the tag;   A.z / B.z  epoch (low / high word)
+//   A.w, B.x, B.y  the 12 input bytes behind the hashed word
+// * tag = word >> 17.  hash = (w ^ (w >> 12)) & 0x1FFFF determines bits 0..16 of w once bits 17..31 are known
+//   (b_i = h_i ^ b_{i+12} downwards), so "same slot and same tag" is EXACTLY "same 4-byte word": the hit test of
+//   :100 and the match length (:126-137) need no access to the candidate's bytes -- the second, dependent DRAM
+//   access of a probe disappears.
+// * an entry counts only if it was written under the current epoch (one per encoded block), which replaces
+//   tsqInit's memset of the table (tsq_context.cpp:77-80): nothing is zeroed per block.
+// * a commit writes the whole sector, so DRAM needs no read-modify-write for it.
+struct Entry { uint4 A, B; };
+
+__device__ __forceinline__ void store_entry(uint4* table, uint32_t h, uint32_t pos, const uint32_t own[4], uint64_t epoch)
 {
-    const uint32_t tag = w >> 17;
-    return make_uint2(pos | (tag << 22), (tag >> 10) | (next4 << 8));
+    const uint32_t tag = own[0] >> 17;
+    table[2u * h]      = make_uint4(pos | (tag << 22), tag >> 10, (uint32_t)epoch, own[1]);
+    table[2u * h + 1u] = make_uint4(own[2], own[3], (uint32_t)(epoch >> 32), 0u);
 }
 
 __device__ __forceinline__ uint32_t lanes_from_to(uint32_t lo, uint32_t hi)   // bits lo..hi inclusive
@@ -301,7 +309,7 @@ struct BlockEncoder {
     }
 };
 
-__device__ uint32_t encode_block_batch(uint2* __restrict__ table, const uint8_t* __restrict__ in, const uint32_t size,
+__device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
                                        uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags)
 {
     BlockEncoder e;
@@ -326,25 +334,20 @@ __device__ uint32_t encode_block_batch(uint2* __restrict__ table, const uint8_t*
         ldg16(in + x, own);
         const uint32_t w = own[0];
         const uint32_t h = hash17(w);
-        const uint2 ent = table[h];
+        const uint4 A = table[2u * h], B = table[2u * h + 1u];
         const uint32_t M = __match_any_sync(FULL, h);
-        // Fat entry (see make_entry): position, the 15 word bits the hash does not determine, and the 3 bytes
-        // behind the word.  An empty entry is the reference's zero entry: candidate = start of the 64 KiB
-        // segment (expand_pos(0, x)), one shared, cache-resident location.
-        const uint32_t p22 = ent.x & 0x3FFFFFu;
+        // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
+        // (expand_pos(0, x)), one shared, cache-resident location.
+        const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
+        const uint32_t p22 = live ? (A.x & 0x3FFFFFu) : 0u;
         const uint32_t tab_cand = expand_pos(p22 & 0xFFFFu, x);
         uint32_t m_tab;
-        bool need_load = true;
-        if ((ent.x | ent.y) != 0u && tab_cand == p22) {
+        if (live && tab_cand == p22) {
             // the entry really describes in[tab_cand]: same hash and same high word bits <=> same word (:100)
-            const uint32_t tag = (ent.x >> 22) | ((ent.y & 31u) << 10);
-            if (tag != (w >> 17)) { m_tab = 0; need_load = false; }
-            else {
-                const uint32_t d = ((ent.y >> 8) ^ own[1]) & 0xFFFFFFu;       // bytes 4..6 behind the word
-                if (d) { m_tab = 4u + (((uint32_t)__ffs((int)d) - 1u) >> 3); need_load = false; }
-            }
-        }
-        if (need_load) {                                               // empty / aliased entry, or a match of >= 7 bytes
+            const uint32_t tag = (A.x >> 22) | (A.y << 10);
+            cb[0] = own[0]; cb[1] = A.w; cb[2] = B.x; cb[3] = B.y;
+            m_tab = tag == (w >> 17) ? prefix16(own, cb) : 0u;
+        } else {                                                       // empty entry, or one older than 64 KiB (aliased)
             ldg16(in + tab_cand, cb);
             m_tab = prefix16(own, cb);                                 // >= 4  <=>  the 4-byte words are equal (:100)
         }
@@ -506,7 +509,7 @@ __device__ uint32_t encode_block_batch(uint2* __restrict__ table, const uint8_t*
         // ---------------- leave the window: commit inserts (last writer per hash wins, :79)
         {
             const uint32_t mine = M & inP;
-            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) table[h] = make_entry(x, w, own[1]);
+            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) store_entry(table, h, x, own, epoch);
             __syncwarp();
         }
         base = chain_pending ? i : i + 1u;
@@ -522,15 +525,14 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= a.n_slots) return;
     WarpWs& ws = ws_all[threadIdx.x >> 5];
-    uint2* table = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(a.tables) + (size_t)slot * kFatTableBytes);
+    uint4* table = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.tables) + (size_t)slot * kFatTableBytes);
+    uint64_t epoch = a.epoch;
     for (uint64_t b = slot; b < a.nb; b += a.n_slots) {
-        uint4* t4 = reinterpret_cast<uint4*>(table);                   // tsqInit (tsq_context.cpp:77-80)
-        for (uint32_t q = lane; q < kFatTableBytes / 16u; q += 32u) t4[q] = make_uint4(0, 0, 0, 0);
-        __syncwarp();
+        epoch++;                                                       // a fresh (empty) table: tsqInit (tsq_context.cpp:77-80)
         const uint64_t at = b * (uint64_t)a.block;
         const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
         uint32_t flags;
-        const uint32_t c = encode_block_batch(table, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
+        const uint32_t c = encode_block_batch(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
         if (lane == 0) { a.sizes[b] = c; if (a.tailflags) a.tailflags[b] = flags; }
         __syncwarp();
     }
