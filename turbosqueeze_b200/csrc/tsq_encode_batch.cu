@@ -97,13 +97,19 @@ __device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4
 // * an entry counts only if it was written under the current epoch (one per encoded block), which replaces
 //   tsqInit's memset of the table (tsq_context.cpp:77-80): nothing is zeroed per block.
 // * a commit writes the whole sector, so DRAM needs no read-modify-write for it.
-struct Entry { uint4 A, B; };
+// Blackwell has 256-bit global loads / stores (SASS LDG.E.ENL2.256 / STG.E.ENL2.256): one request per probe,
+// and a commit that covers its whole sector.
+__device__ __forceinline__ void load_entry(const uint4* table, uint32_t h, uint4& A, uint4& B)
+{
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h) : "memory");
+}
 
 __device__ __forceinline__ void store_entry(uint4* table, uint32_t h, uint32_t pos, const uint32_t own[4], uint64_t epoch)
 {
     const uint32_t tag = own[0] >> 17;
-    table[2u * h]      = make_uint4(pos | (tag << 22), tag >> 10, (uint32_t)epoch, own[1]);
-    table[2u * h + 1u] = make_uint4(own[2], own[3], (uint32_t)(epoch >> 32), 0u);
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(table + 2u * h), "r"(pos | (tag << 22)), "r"(tag >> 10),
+                 "r"((uint32_t)epoch), "r"(own[1]), "r"(own[2]), "r"(own[3]), "r"((uint32_t)(epoch >> 32)), "r"(0u) : "memory");
 }
 
 __device__ __forceinline__ uint32_t lanes_from_to(uint32_t lo, uint32_t hi)   // bits lo..hi inclusive
@@ -334,7 +340,8 @@ __device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t
         ldg16(in + x, own);
         const uint32_t w = own[0];
         const uint32_t h = hash17(w);
-        const uint4 A = table[2u * h], B = table[2u * h + 1u];
+        uint4 A, B;
+        load_entry(table, h, A, B);
         const uint32_t M = __match_any_sync(FULL, h);
         // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
         // (expand_pos(0, x)), one shared, cache-resident location.
