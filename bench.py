@@ -303,10 +303,10 @@ def run_ours(args):
             "encode_gbs": round(enc_gbs, 3), "decode_gbs": round(dec_gbs, 3), "ms_encode": round(ms_enc, 4), "ms_decode": round(ms_dec, 4),
             "bit_exact_round_trip": ok,
             "roofline": {"kernel": "encode_batch_kernel", "bound": "hbm", "achieved": round(enc_ach, 2), "peak": hbm_peak, "unit": "GB/s",
-                         "frac": round(enc_ach / hbm_peak, 5), "traffic": args.traffic_encode, "peak_source": peak_src,
+                         "frac": round(enc_ach / hbm_peak, 5), "traffic": args.traffic_encode if name == "enwik9-shape-1GB-256KiB" else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": int(alg), "share_of_step": round(ms_enc / (ms_enc + ms_dec), 4)},
             "roofline_decode": {"kernel": "decode_split_kernel", "bound": "hbm", "achieved": round(dec_ach, 2), "peak": hbm_peak, "unit": "GB/s",
-                                "frac": round(dec_ach / hbm_peak, 5), "traffic": args.traffic_decode,
+                                "frac": round(dec_ach / hbm_peak, 5), "traffic": args.traffic_decode if name == "enwik9-shape-1GB-256KiB" else None,
                                 "algorithmic_bytes_per_launch": int(alg), "share_of_step": round(ms_dec / (ms_enc + ms_dec), 4)},
             "e2e": {"value": round(e2e_value, 3), "unit": "GB/s", "h2d_bytes_per_step": int(total + clen), "d2h_bytes_per_step": int(clen + total),
                     "call": "tsqb_compress_into + tsqb_decompress_into (pinned host buffers)", "steps": e2e_steps, "round_trip_ok": e2e_ok,
@@ -343,8 +343,10 @@ def main():
     ap.add_argument("--cpu-sample-mb", type=int, default=1024, help="bytes of the workload the CPU baseline is timed on")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--traffic-encode", type=float, default=None, help="dram bytes per launch from an ncu --set full capture")
-    ap.add_argument("--traffic-decode", type=float, default=None)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 1 GB workload, from the committed ncu --set full
+    # capture profiles/r01_v4_ncu_full_summary.txt (a profiler figure cannot be measured inside a timed run)
+    ap.add_argument("--traffic-encode", type=float, default=124.83e9, help="dram bytes per launch from an ncu --set full capture")
+    ap.add_argument("--traffic-decode", type=float, default=6.01e9)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
