@@ -82,7 +82,7 @@ struct tsqb_context {
     cudaStream_t stream = nullptr;
     // pipelined host path: copy-in / copy-out streams, one compute stream + events per chunk in flight
     static constexpr int kPipe = 4;
-    cudaStream_t s_in = nullptr, s_out = nullptr, s_chunk[kPipe] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_chunk[kPipe] = {};
     cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
     uint64_t* h_len = nullptr;                 // pinned: per-chunk container length
     int pipeline = 1;                          // 0: one-shot staging (round-1 v1 behaviour)
