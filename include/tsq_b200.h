@@ -74,7 +74,8 @@ uint64_t tsqb_slot_stride(uint32_t block_size);
 
 /* Kernel selection knobs (for benchmarking / tests).  key: "encode_impl" (0 = auto, 1 = scalar
  * thread-per-block, 2 = warp-per-block byte emitter, 3 = warp-per-block token batches), "decode_lanes" (0 = auto, else 1,2,4,8,16,32 lanes per
- * block), "encode_slots" (0 = auto: concurrent hash tables), "pipeline" (1 = the host-buffer calls overlap
+ * block), "encode_slots" (0 = auto: concurrent hash tables), "encode_fat" (batch encoder table format: -1 = auto, 0 = u16 tables, 1 = 32-byte sector
+ * entries), "pipeline" (1 = the host-buffer calls overlap
  * PCIe copies with kernels in chunks, 0 = one-shot staging), "pipeline_min" (bytes below which one-shot is used).  Returns 0 when the key is known. */
 int tsqb_set_option(tsqb_context* ctx, const char* key, int64_t value);
 

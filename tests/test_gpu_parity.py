@@ -234,6 +234,24 @@ def test_container_pack_index_and_buffer_api(torch, ctx, oracle):
         assert T.tsq_decompress_mt(ref.compress_mt(buf[:n], 1)) == buf[:n].tobytes()   # and we read its
 
 
+@pytest.mark.parametrize("fat", [0, 1], ids=["u16-tables", "sector-entries"])
+def test_batch_encoder_table_formats_are_bit_exact(torch, ctx, checker, fat):
+    """The batch encoder keeps the reference's 2^17 x u16 table when few blocks are in flight (L2-resident) and
+    32-byte sector entries (exact word tag + 12 bytes + epoch, no zeroing) otherwise: same bytes either way."""
+    ctx.set_option("encode_fat", fat)
+    try:
+        for kind, n, block in [("text", (3 << 20) + 777, 4096), ("text", (2 << 20) + 5, 262144), ("rep8", 1 << 20, 65536),
+                               ("random", (1 << 20) + 3, 16384), ("runs", 300000, 300000), ("text", 70000, 70000)]:
+            buf = make_input(kind, n, seed=n + 11)
+            want_slots, want_sizes, _ = checker.encode_blocks(buf, n, block, 0)
+            for rep in range(2):                                   # second pass: tables hold entries of older epochs
+                got_slots, got_sizes = gpu_encode(torch, ctx, buf, n, block, 0, 3)
+                assert_streams_equal(got_slots, got_sizes, want_slots, want_sizes, block, (kind, n, block, fat, rep))
+    finally:
+        ctx.set_option("encode_fat", -1)
+        ctx.set_option("encode_impl", 0)
+
+
 def test_pipelined_host_path_equals_one_shot(torch, ctx):
     """The chunked, stream-overlapped host path (H2D | kernels | D2H) must produce the very same container
     as one-shot staging, including the bytes a chunk's last block reads from the next chunk."""

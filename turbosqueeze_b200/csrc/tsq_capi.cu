@@ -74,6 +74,7 @@ struct tsqb_context {
     int encode_impl = 0;       // 0 auto, 1 scalar, 2 warp
     int decode_lanes = 0;      // 0 auto
     int64_t encode_slots = 0;  // 0 auto
+    int encode_fat = -1;       // batch encoder table format: -1 auto, 0 u16 tables, 1 sector entries
     DevBuf tables;             // hash tables of the blocks in flight (zeroed when allocated: epoch 0 = empty)
     DevBuf ftables;            // batch encoder: 32-byte entries, only ever written by that kernel, zeroed at allocation
     uint64_t launch_id = 0;    // encode launches so far: the epoch of the batch encoder's table entries
@@ -153,6 +154,7 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
     if (!strcmp(key, "encode_impl"))  { c->encode_impl = (int)v; return 0; }
     if (!strcmp(key, "decode_lanes")) { c->decode_lanes = (int)v; return 0; }
     if (!strcmp(key, "encode_slots")) { c->encode_slots = v; return 0; }
+    if (!strcmp(key, "encode_fat")) { c->encode_fat = (int)v; return 0; }
     if (!strcmp(key, "pipeline")) { c->pipeline = (int)v; return 0; }
     if (!strcmp(key, "pipeline_min")) { c->pipeline_min = (uint64_t)v; return 0; }
     if (!strcmp(key, "l2_fetch")) {                                  // 32 / 64 / 128: DRAM fetch granularity hint
@@ -180,10 +182,11 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.epoch = (++c->launch_id) << 20;                                 // + the slot's block counter, < 2^20
     const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
-    if (tables) a.tables = tables;
+    a.fat = (c->encode_fat < 0 ? encode_wants_fat(impl, a.n_slots) : (impl == 3 && c->encode_fat != 0)) ? 1u : 0u;
+    if (tables) { a.tables = tables; a.fat = impl == 3 ? 1u : 0u; }            // the pipelined path provisions sector tables
     else {
-        DevBuf& tb = impl == 3 ? c->ftables : c->tables;
-        if (tb.ensure((size_t)a.n_slots * encode_table_bytes(impl))) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
+        DevBuf& tb = a.fat ? c->ftables : c->tables;
+        if (tb.ensure((size_t)a.n_slots * encode_table_bytes(impl, a.fat != 0))) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
         a.tables = (uint16_t*)tb.p;
     }
     CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
@@ -352,7 +355,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     }
     const uint64_t ccap = 16 + per * (stride + 3) + 256;                     // container capacity of one chunk
     if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
-        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || (impl == 3 ? c->ftables : c->tables).ensure(tab_total * encode_table_bytes(impl)))
+        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || (impl == 3 ? c->ftables : c->tables).ensure(tab_total * encode_table_bytes(impl, true)))
         return fail("compress: out of device memory");
     uint8_t* d_in = (uint8_t*)c->in.p;
     CU(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
@@ -369,7 +372,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
         CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
         // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
         if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
-                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl)))) return 1;
+                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)))) return 1;
         uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
         uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
         CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,

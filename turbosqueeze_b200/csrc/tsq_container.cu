@@ -21,7 +21,10 @@ uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_over
     return (uint32_t)slots;
 }
 
-uint32_t encode_table_bytes(int impl) { return impl == 3 ? kFatTableBytes : kTableBytes; }
+uint32_t encode_table_bytes(int impl, bool fat) { return impl == 3 && fat ? kFatTableBytes : kTableBytes; }
+
+// 384 tables x (256 KiB + a 64 KiB back-window) = 120 MB: what the 126 MB L2 can keep resident
+bool encode_wants_fat(int impl, uint32_t n_slots) { return impl == 3 && n_slots > 384u; }
 
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int /*sm_count*/, cudaStream_t st)
 {

@@ -22,6 +22,7 @@ struct EncodeArgs {
     uint32_t*      tailflags; // optional: kTail* flags per block (see tsq_encode_common.cuh)
     uint16_t*      tables;    // n_slots tables (kTableBytes each; kFatTableBytes for the batch encoder)
     uint64_t       epoch;     // batch encoder: entries written under another epoch are empty (no per-block zeroing)
+    uint32_t       fat;       // batch encoder: 1 = sector entries (kFatTableBytes per table), 0 = u16 tables
     uint32_t       n_slots;
 };
 
@@ -40,7 +41,9 @@ struct DecodeArgs {
 // 3 = warp per block with token batches (tsq_encode_batch.cu, the default without extensions).
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int sm_count, cudaStream_t st);
 // bytes of one hash table of launch_encode(impl)
-uint32_t    encode_table_bytes(int impl);
+uint32_t    encode_table_bytes(int impl, bool fat);
+// batch encoder: sector entries pay off once the tables no longer fit the L2
+bool        encode_wants_fat(int impl, uint32_t n_slots);
 // how many hash tables launch_encode(impl) will use for nb blocks (caller sizes a.tables from it)
 uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);
 

@@ -315,7 +315,11 @@ struct BlockEncoder {
     }
 };
 
-__device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
+// FAT = sector entries in a 4 MiB table (thousands of blocks in flight: the tables live in HBM and a probe must
+// not need a second, dependent access); !FAT = the reference's own 2^17 x u16 table, zeroed per block, for a few
+// hundred blocks in flight, whose tables (256 KiB each) and 64 KiB back-windows stay resident in the 126 MB L2.
+template <bool FAT>
+__device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
                                        uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags)
 {
     BlockEncoder e;
@@ -328,6 +332,8 @@ __device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t
     if (lane < 3) e.ring_put(lane + e.oal, size >> (8u * lane));              // tsq_encode.cpp:53-55
     __syncwarp();
 
+    uint4* const table = static_cast<uint4*>(table_);                  // FAT
+    uint16_t* const table16 = static_cast<uint16_t*>(table_);           // !FAT
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t i = 0, lit_from = 0;
     uint32_t base = 1;                // first probe is position 1 (:70-72)
@@ -340,23 +346,29 @@ __device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t
         ldg16(in + x, own);
         const uint32_t w = own[0];
         const uint32_t h = hash17(w);
-        uint4 A, B;
-        load_entry(table, h, A, B);
         const uint32_t M = __match_any_sync(FULL, h);
-        // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
-        // (expand_pos(0, x)), one shared, cache-resident location.
-        const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
-        const uint32_t p22 = live ? (A.x & 0x3FFFFFu) : 0u;
-        const uint32_t tab_cand = expand_pos(p22 & 0xFFFFu, x);
-        uint32_t m_tab;
-        if (live && tab_cand == p22) {
-            // the entry really describes in[tab_cand]: same hash and same high word bits <=> same word (:100)
-            const uint32_t tag = (A.x >> 22) | (A.y << 10);
-            cb[0] = own[0]; cb[1] = A.w; cb[2] = B.x; cb[3] = B.y;
-            m_tab = tag == (w >> 17) ? prefix16(own, cb) : 0u;
-        } else {                                                       // empty entry, or one older than 64 KiB (aliased)
+        uint32_t tab_cand, m_tab;
+        if constexpr (FAT) {
+            uint4 A, B;
+            load_entry(table, h, A, B);
+            // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
+            // (expand_pos(0, x)), one shared, cache-resident location.
+            const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
+            const uint32_t p22 = live ? (A.x & 0x3FFFFFu) : 0u;
+            tab_cand = expand_pos(p22 & 0xFFFFu, x);
+            if (live && tab_cand == p22) {
+                // the entry really describes in[tab_cand]: same hash and same high word bits <=> same word (:100)
+                const uint32_t tag = (A.x >> 22) | (A.y << 10);
+                cb[0] = own[0]; cb[1] = A.w; cb[2] = B.x; cb[3] = B.y;
+                m_tab = tag == (w >> 17) ? prefix16(own, cb) : 0u;
+            } else {                                                   // empty entry, or one older than 64 KiB (aliased)
+                ldg16(in + tab_cand, cb);
+                m_tab = prefix16(own, cb);                             // >= 4  <=>  the 4-byte words are equal (:100)
+            }
+        } else {
+            tab_cand = expand_pos(table16[h], x);                      // :76-78
             ldg16(in + tab_cand, cb);
-            m_tab = prefix16(own, cb);                                 // >= 4  <=>  the 4-byte words are equal (:100)
+            m_tab = prefix16(own, cb);
         }
         const bool anydup = __any_sync(FULL, M != (1u << lane));
         uint32_t inP = 0, c = 0;
@@ -516,7 +528,10 @@ __device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t
         // ---------------- leave the window: commit inserts (last writer per hash wins, :79)
         {
             const uint32_t mine = M & inP;
-            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) store_entry(table, h, x, own, epoch);
+            if (((inP >> lane) & 1u) && (mine >> lane) == 1u) {
+                if constexpr (FAT) store_entry(table, h, x, own, epoch);
+                else table16[h] = (uint16_t)x;
+            }
             __syncwarp();
         }
         base = chain_pending ? i : i + 1u;
@@ -525,6 +540,7 @@ __device__ uint32_t encode_block_batch(uint4* __restrict__ table, const uint64_t
     return e.finish(flags);
 }
 
+template <bool FAT>
 __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
 {
     __shared__ WarpWs ws_all[kWarps];
@@ -532,14 +548,19 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
     const uint32_t slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (slot >= a.n_slots) return;
     WarpWs& ws = ws_all[threadIdx.x >> 5];
-    uint4* table = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(a.tables) + (size_t)slot * kFatTableBytes);
+    uint8_t* table = reinterpret_cast<uint8_t*>(a.tables) + (size_t)slot * (FAT ? kFatTableBytes : kTableBytes);
     uint64_t epoch = a.epoch;
     for (uint64_t b = slot; b < a.nb; b += a.n_slots) {
-        epoch++;                                                       // a fresh (empty) table: tsqInit (tsq_context.cpp:77-80)
+        if constexpr (FAT) epoch++;                                    // a fresh (empty) table: tsqInit (tsq_context.cpp:77-80)
+        else {
+            uint4* t4 = reinterpret_cast<uint4*>(table);
+            for (uint32_t q = lane; q < kTableBytes / 16u; q += 32u) t4[q] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+        }
         const uint64_t at = b * (uint64_t)a.block;
         const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
         uint32_t flags;
-        const uint32_t c = encode_block_batch(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
+        const uint32_t c = encode_block_batch<FAT>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
         if (lane == 0) { a.sizes[b] = c; if (a.tailflags) a.tailflags[b] = flags; }
         __syncwarp();
     }
@@ -551,7 +572,8 @@ cudaError_t launch_encode_batch(const EncodeArgs& a, cudaStream_t st)
 {
     if (a.nb == 0) return cudaSuccess;
     const unsigned ctas = (a.n_slots + kWarps - 1) / kWarps;
-    encode_batch_kernel<<<ctas, kWarps * 32, 0, st>>>(a);
+    if (a.fat) encode_batch_kernel<true><<<ctas, kWarps * 32, 0, st>>>(a);
+    else       encode_batch_kernel<false><<<ctas, kWarps * 32, 0, st>>>(a);
     return cudaGetLastError();
 }
 
