@@ -139,15 +139,15 @@ static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream
 }
 
 cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
-cudaError_t launch_decode_split(const DecodeArgs& a, int sm_count, cudaStream_t st);
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st);
 
 // lanes: 0 = auto; 34 = walker + copier kernel (tsq_decode_split.cu, the default without extensions);
 // 1..32 = sub-warp kernel with that many lanes per block; 33 = force the warp-per-block
 // step kernel (tsq_decode_warp.cu), 32 = force the pair-step kernel at full warp width
 cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st)
 {
-    if (lanes <= 0) lanes = ext ? decode_lanes_auto(a.nb, sm_count) : 34;
-    if (lanes == 34) return ext ? cudaErrorInvalidValue : launch_decode_split(a, sm_count, st);
+    if (lanes <= 0) lanes = 34;
+    if (lanes == 34) return launch_decode_split(a, ext, sm_count, st);
     if (lanes == 33) return ext ? cudaErrorInvalidValue : launch_decode_warp(a, sm_count, st);
 #define TSQB_CASE(Wv) case Wv: return ext ? launch_decode_t<Wv, true>(a, sm_count, st) : launch_decode_t<Wv, false>(a, sm_count, st);
     switch (lanes) {

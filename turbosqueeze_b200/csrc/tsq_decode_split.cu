@@ -1,6 +1,7 @@
-// tsq_decode_split.cu -- the production no-extension decoder: one WALKER lane + one COPIER warp per block.
+// tsq_decode_split.cu -- the production decoder (both formats): one WALKER lane + one COPIER warp per block.
 //
-// Semantics: reference tsqDecodeNoext (tsq_decode.cpp:42-126), bit-exact on [0, size).
+// Semantics: reference tsqDecodeNoext (tsq_decode.cpp:42-126) and the extension variant (:137-314, template
+// EXT: matches of 32 / 48 / 64 bytes), bit-exact on [0, size).
 //
 // Why two roles.  The token walk is a serial chain: the address of every size byte depends on the
 // payload lengths of the pair before it (tsq_decode.cpp:68-86), ~50 cycles per pair even from
@@ -135,6 +136,15 @@ __device__ __forceinline__ uint2 ld_vol_u64(const uint2* p)
     return v;
 }
 
+// decoded length of a symbol: size nibble + 1, except that in the extension format a match with nibble 0 / 1 / 2
+// is 32 / 48 / 64 bytes long (tsq_decode.cpp:174-187)
+template <bool EXT>
+__device__ __forceinline__ uint32_t sym_len(uint32_t nibble, bool lit)
+{
+    if (EXT && !lit && nibble < 3u) return 16u * (nibble + 2u);
+    return nibble + 1u;
+}
+
 // where block b's stream starts / how many bytes of it may be read
 __device__ __forceinline__ const uint8_t* stream_of(const DecodeArgs& a, uint64_t b, uint32_t& limit)
 {
@@ -146,7 +156,7 @@ __device__ __forceinline__ const uint8_t* stream_of(const DecodeArgs& a, uint64_
 // Lane L walks the token stream of slot L.  All lanes run the same loop; a lane that has to wait
 // (stream chunk not landed, descriptor queue full, copier still setting the block up) simply does
 // nothing in that iteration.
-template <uint32_t OUT_RING>
+template <uint32_t OUT_RING, bool EXT>
 __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t nslots, uint32_t widx, unsigned lane)
 {
     enum { P_DONE = 0, P_WAIT = 1, P_WALK = 2 };
@@ -196,7 +206,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                 const uint32_t p_safe = min(have, limit_al);
                 int groups = 0;
 #pragma unroll 1
-                while (groups < 4 && (k & 3u) == 0 && p + 4u * kLook <= p_safe && (k - cons) + 4u <= kQueue && j + 128u < size) {
+                while (groups < 4 && (k & 3u) == 0 && p + 4u * kLook <= p_safe && (k - cons) + 4u <= kQueue && j + (EXT ? 512u : 128u) < size) {
                     const uint32_t dsl = dbase + ((k & kQMask) << 3);
                     const uint32_t c = ring_u8(p);                                  // :62
                     uint32_t pp = p + 1u;
@@ -208,7 +218,8 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                         const uint32_t pay0 = (c & (0x80u >> (2 * q))) ? n0 + 2u : 3u;   // payload + the size byte itself
                         const uint32_t pay1 = (c & (0x40u >> (2 * q))) ? n1 + 1u : 2u;
                         pp += pay0 + pay1;
-                        j += n0 + n1 + 2u;
+                        if (EXT) j += sym_len<true>(n0, (c & (0x80u >> (2 * q))) != 0) + sym_len<true>(n1, (c & (0x40u >> (2 * q))) != 0);
+                        else     j += n0 + n1 + 2u;
                     }
                     p = pp;
                     k += 4u;
@@ -229,10 +240,10 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     const uint32_t n0 = nib >> 4, n1 = nib & 15u;
                     const uint32_t pay0 = (ctl & (0x80u >> (2u * q))) ? n0 + 1u : 2u;
                     const uint32_t pay1 = (ctl & (0x40u >> (2u * q))) ? n1 + 1u : 2u;
-                    const uint32_t j1 = j + n0 + 1u;
+                    const uint32_t j1 = j + sym_len<EXT>(n0, (ctl & (0x80u >> (2u * q))) != 0);
                     const bool two = j1 < size;                                     // second symbol exists
                     p = pp + 1u + pay0 + (two ? pay1 : 0u);
-                    j = j1 + (two ? n1 + 1u : 0u);
+                    j = j1 + (two ? sym_len<EXT>(n1, (ctl & (0x40u >> (2u * q))) != 0) : 0u);
                     k++;
                     st_vol_u32(&sm.produced, k);
                     if ((k & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
@@ -299,7 +310,7 @@ __device__ __forceinline__ void store16_desc(uint32_t base, uint32_t mask, uint3
     }
 }
 
-template <uint32_t OUT_RING>
+template <uint32_t OUT_RING, bool EXT>
 __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slot, uint32_t nslots, unsigned lane)
 {
     constexpr uint32_t kOMask = OUT_RING - 1;
@@ -433,8 +444,8 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                     const uint32_t n0 = nib >> 4, n1 = nib & 15u;
                     const bool l0 = (d.x & (0x80u << 18)) != 0, l1 = (d.x & (0x40u << 18)) != 0;
                     uint32_t dst;
-                    if (half == 0) { lit = l0; len = n0 + 1u; sp = pp + 1u; dst = jp; }
-                    else { lit = l1; len = n1 + 1u; sp = pp + 1u + (l0 ? n0 + 1u : 2u); dst = jp + n0 + 1u; }
+                    if (half == 0) { lit = l0; len = sym_len<EXT>(n0, l0); sp = pp + 1u; dst = jp; }
+                    else { lit = l1; len = sym_len<EXT>(n1, l1); sp = pp + 1u + (l0 ? n0 + 1u : 2u); dst = jp + sym_len<EXT>(n0, l0); }
                     active = active && dst < size;
                     len = active ? min(len, size - dst) : 0u;
                     q = dst + oal;
@@ -451,7 +462,10 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                 // Literals and near matches both come out of shared memory (stream ring / output ring);
                 // far matches read bytes an earlier step flushed to HBM.
                 uint32_t v[4] = {0, 0, 0, 0};
-                bool now = active && (lit || srcq + len <= J0);
+                // extension format: a match of 32 / 48 / 64 bytes does not fit a lane's 16-byte run; it takes the
+                // in-order lane-per-byte path below, from the output ring or -- when older than the ring -- from HBM
+                const bool longsym = EXT && len > 16u;
+                bool now = active && !longsym && (lit || srcq + len <= J0);
                 bool pending = active && !now;
                 bool placed = false;                                             // v[] holds this symbol's bytes
                 const bool far = now && !lit && srcq + OUT_RING < J1 + 16u;
@@ -485,10 +499,12 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                     __syncwarp();                                                // stores so far are visible to the warp
                     const uint32_t pl = (uint32_t)__ffs((int)pm) - 1u;
                     const uint32_t s_q = __shfl_sync(FULL, q, pl), s_src = __shfl_sync(FULL, srcq, pl), s_len = __shfl_sync(FULL, len, pl);
-                    if (lane < s_len) {
+                    const bool s_far = EXT && s_src + OUT_RING < J1 + 16u;        // only long matches can be far here
+                    for (uint32_t t = lane; t < s_len; t += 32u) {     // one trip without extensions (s_len <= 16)
                         uint32_t byte;
-                        asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + lane) & kOMask)) : "memory");
-                        asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + lane) & kOMask)), "r"(byte) : "memory");
+                        if (EXT && s_far) byte = __ldcg(o_al + s_src + t);
+                        else asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + t) & kOMask)) : "memory");
+                        asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + t) & kOMask)), "r"(byte) : "memory");
                     }
                     pm &= pm - 1u;
                 }
@@ -510,7 +526,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
     }
 }
 
-template <uint32_t OUT_RING>
+template <uint32_t OUT_RING, bool EXT>
 __global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uint32_t nslots)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -529,37 +545,44 @@ __global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uin
         }
     }
     __syncthreads();
-    if (wid < nslots) copier<OUT_RING>(a, slots[wid], wid, nslots, lane);
-    else              walker<OUT_RING>(a, slots, nslots, wid - nslots, lane);
+    if (wid < nslots) copier<OUT_RING, EXT>(a, slots[wid], wid, nslots, lane);
+    else              walker<OUT_RING, EXT>(a, slots, nslots, wid - nslots, lane);
 }
 
-template <uint32_t OUT_RING>
+template <uint32_t OUT_RING, bool EXT>
 cudaError_t launch_split_t(const DecodeArgs& a, uint32_t nslots, unsigned ctas, cudaStream_t st)
 {
     const size_t smem = sizeof(SlotSmem<OUT_RING>) * nslots;
-    cudaError_t e = cudaFuncSetAttribute(decode_split_kernel<OUT_RING>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_split_kernel<OUT_RING, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    decode_split_kernel<OUT_RING><<<ctas, (nslots + kWalkers) * 32, smem, st>>>(a, nslots);
+    decode_split_kernel<OUT_RING, EXT><<<ctas, (nslots + kWalkers) * 32, smem, st>>>(a, nslots);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 // One CTA per SM; every CTA owns `nslots` block slots (copier warps) and kWalkers walker warps.
-cudaError_t launch_decode_split(const DecodeArgs& a, int sm_count, cudaStream_t st)
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st)
 {
     if (a.nb == 0) return cudaSuccess;
+    const size_t budget = 227u * 1024u;
     uint64_t per_sm = (a.nb + sm_count - 1) / sm_count;
     uint32_t nslots = (uint32_t)(per_sm < kMaxSlots ? per_sm : kMaxSlots);
     if (nslots == 0) nslots = 1;
+    // a step of the extension format can produce 32 x 64 bytes: the output ring must be >= 4 KiB
+    if (ext) while (sizeof(SlotSmem<4096>) * nslots > budget) nslots--;
     unsigned ctas = (unsigned)((a.nb + nslots - 1) / nslots);
     if (ctas > (unsigned)sm_count) ctas = (unsigned)sm_count;
     // output ring as large as 227 KB of shared memory allows
-    const size_t budget = 227u * 1024u;
-    if (sizeof(SlotSmem<16384>) * nslots <= budget) return launch_split_t<16384>(a, nslots, ctas, st);
-    if (sizeof(SlotSmem<8192>) * nslots <= budget)  return launch_split_t<8192>(a, nslots, ctas, st);
-    if (sizeof(SlotSmem<4096>) * nslots <= budget)  return launch_split_t<4096>(a, nslots, ctas, st);
-    return launch_split_t<2048>(a, nslots, ctas, st);
+    if (ext) {
+        if (sizeof(SlotSmem<16384>) * nslots <= budget) return launch_split_t<16384, true>(a, nslots, ctas, st);
+        if (sizeof(SlotSmem<8192>) * nslots <= budget)  return launch_split_t<8192, true>(a, nslots, ctas, st);
+        return launch_split_t<4096, true>(a, nslots, ctas, st);
+    }
+    if (sizeof(SlotSmem<16384>) * nslots <= budget) return launch_split_t<16384, false>(a, nslots, ctas, st);
+    if (sizeof(SlotSmem<8192>) * nslots <= budget)  return launch_split_t<8192, false>(a, nslots, ctas, st);
+    if (sizeof(SlotSmem<4096>) * nslots <= budget)  return launch_split_t<4096, false>(a, nslots, ctas, st);
+    return launch_split_t<2048, false>(a, nslots, ctas, st);
 }
 
 }  // namespace tsqb
