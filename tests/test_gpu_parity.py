@@ -81,7 +81,7 @@ def golden_input(g):
     return buf
 
 
-@pytest.mark.parametrize("impl,ext", [(3, 0), (2, 0), (1, 0), (1, 1)], ids=["batch", "warp", "scalar", "scalar-ext"])
+@pytest.mark.parametrize("impl,ext", [(3, 0), (3, 1), (2, 0), (1, 0), (1, 1)], ids=["batch", "batch-ext", "warp", "scalar", "scalar-ext"])
 def test_encode_matches_reference_golden_vectors(torch, ctx, impl, ext):
     """tests/golden/golden_blocks.json was produced by the compiled unmodified reference."""
     for g in GOLDEN:
@@ -106,7 +106,7 @@ CASES = [(1, 1), (2, 2), (5, 5), (31, 31), (32, 32), (33, 33), (34, 34), (63, 64
 
 
 @pytest.mark.parametrize("kind", ["text", "random", "rep8", "zeros", "runs"])
-@pytest.mark.parametrize("impl,ext", [(3, 0), (2, 0), (1, 0), (1, 1)], ids=["batch", "warp", "scalar", "scalar-ext"])
+@pytest.mark.parametrize("impl,ext", [(3, 0), (3, 1), (2, 0), (1, 0), (1, 1)], ids=["batch", "batch-ext", "warp", "scalar", "scalar-ext"])
 def test_encode_bit_exact_vs_oracle(torch, ctx, checker, kind, impl, ext):
     rng = np.random.default_rng(11)
     cases = CASES + [(int(rng.integers(1, 400000)), int(rng.integers(1, 300000))) for _ in range(6)]
@@ -277,21 +277,22 @@ def test_pipelined_host_path_equals_one_shot(torch, ctx):
         ctx.set_option("pipeline_min", 64 << 20)
 
 
-@pytest.mark.parametrize("kind,block", [("text", 262144), ("random", 262144), ("rep8", 1 << 20), ("text", 4096)])
-def test_large_buffers_bit_exact_and_round_trip(torch, ctx, checker, kind, block):
+@pytest.mark.parametrize("kind,block,ext", [("text", 262144, 0), ("random", 262144, 0), ("rep8", 1 << 20, 0), ("text", 4096, 0),
+                                            ("text", 262144, 1), ("rep8", 65536, 1)])
+def test_large_buffers_bit_exact_and_round_trip(torch, ctx, checker, kind, block, ext):
     """BASELINE.json shapes at a size the multi-threaded reference finishes in seconds (256 MiB):
     every stream byte equals the reference's, and decode(encode(x)) == x on the device."""
     n = (256 << 20) + 54321
     buf = W.fill(kind, n, seed=2024)
     ctx.set_option("encode_impl", 0)
     d = torch.from_numpy(buf).cuda()
-    slots, sizes = ctx.encode_blocks(d, n, block, 0)
-    out, osz = ctx.decode_blocks(slots, sizes.numel(), block, 0, comp_sizes=sizes)
+    slots, sizes = ctx.encode_blocks(d, n, block, ext)
+    out, osz = ctx.decode_blocks(slots, sizes.numel(), block, ext, comp_sizes=sizes)
     torch.cuda.synchronize()
     assert int(osz.sum().item()) == n
     assert torch.equal(out[:n], d[:n])
     threads = os.cpu_count() or 8
-    want_slots, want_sizes, _ = checker.encode_blocks(buf, n, block, 0, threads=threads)
+    want_slots, want_sizes, _ = checker.encode_blocks(buf, n, block, ext, threads=threads)
     got_sizes = sizes.cpu().numpy().astype(np.uint32)
     assert np.array_equal(got_sizes, want_sizes)
-    assert_streams_equal(slots.cpu().numpy(), got_sizes, want_slots, want_sizes, block, (kind, block))
+    assert_streams_equal(slots.cpu().numpy(), got_sizes, want_slots, want_sizes, block, (kind, block, ext))

@@ -180,7 +180,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
     a.epoch = (++c->launch_id) << 20;                                 // + the slot's block counter, < 2^20
-    const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
+    const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
     a.fat = (c->encode_fat < 0 ? encode_wants_fat(impl, a.n_slots) : (impl == 3 && c->encode_fat != 0)) ? 1u : 0u;
     if (tables) { a.tables = tables; a.fat = impl == 3 ? 1u : 0u; }            // the pipelined path provisions sector tables
@@ -346,7 +346,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
     const uint64_t per = (nb + K - 1) / K;                                   // blocks per chunk
     const int nchunks = (int)((nb + per - 1) / per);
-    const int impl = (c->encode_impl == 1 || with_ext) ? 1 : (c->encode_impl == 2 ? 2 : 3);
+    const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
     uint64_t slots_tab[K], tab_at[K], tab_total = 0;
     for (int k = 0; k < nchunks; k++) {
         const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;

@@ -8,7 +8,7 @@ namespace tsqb {
 
 cudaError_t launch_encode_scalar(const EncodeArgs& a, bool ext, cudaStream_t st);
 cudaError_t launch_encode_warp(const EncodeArgs& a, cudaStream_t st);
-cudaError_t launch_encode_batch(const EncodeArgs& a, cudaStream_t st);
+cudaError_t launch_encode_batch(const EncodeArgs& a, bool ext, cudaStream_t st);
 
 uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override)
 {
@@ -28,9 +28,9 @@ bool encode_wants_fat(int impl, uint32_t n_slots) { return impl == 3 && n_slots 
 
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int /*sm_count*/, cudaStream_t st)
 {
-    if (impl == 1 || ext) return launch_encode_scalar(a, ext, st);
-    if (impl == 2) return launch_encode_warp(a, st);
-    return launch_encode_batch(a, st);
+    if (impl == 1) return launch_encode_scalar(a, ext, st);
+    if (impl == 2) return ext ? cudaErrorInvalidValue : launch_encode_warp(a, st);
+    return launch_encode_batch(a, ext, st);
 }
 
 // ---- pack: offsets = exclusive scan of (3 + size), one CTA (n_blocks is at most a few million)

@@ -1,7 +1,8 @@
-// tsq_encode_batch.cu -- the production no-extension encoder: one WARP per block, decisions first,
+// tsq_encode_batch.cu -- the production encoder (both formats): one WARP per block, decisions first,
 // bytes later.
 //
-// Reference semantics: tsqEncodeNoext (tsq_encode.cpp:48-189); bit-exact, see SURVEY.md 8(a).
+// Reference semantics: tsqEncodeNoext (tsq_encode.cpp:48-189) and the extension variant (:200-341, template EXT:
+// match lengths up to 64, mlen[] of :44-45); bit-exact, see SURVEY.md 8(a).
 //
 // The greedy parse is a serial chain (every probe reads a table entry written by an earlier probe,
 // tsq_encode.cpp:74-79), so the warp spends its time in a warp-uniform decision loop.  This kernel
@@ -159,9 +160,9 @@ struct BlockEncoder {
         } while (upto - from > 0);
     }
 
-    __device__ __forceinline__ void match(uint32_t offset, uint32_t k, uint32_t in_pos_after)
+    __device__ __forceinline__ void match(uint32_t offset, uint32_t nibble, uint32_t in_pos_after)
     {
-        push(((k - 1u) << 27) | offset);
+        push((nibble << 27) | offset);
         symbol_done(in_pos_after);
     }
 
@@ -318,7 +319,7 @@ struct BlockEncoder {
 // FAT = sector entries in a 4 MiB table (thousands of blocks in flight: the tables live in HBM and a probe must
 // not need a second, dependent access); !FAT = the reference's own 2^17 x u16 table, zeroed per block, for a few
 // hundred blocks in flight, whose tables (256 KiB each) and 64 KiB back-windows stay resident in the 126 MB L2.
-template <bool FAT>
+template <bool FAT, bool EXT>
 __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
                                        uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags)
 {
@@ -380,11 +381,14 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         // and the source cannot reach the pair start (:139-141); x + 16 < size - 5 keeps the end-of-block
         // conditions (:170-172) out of the picture.  A lane whose hash occurs twice in the window is left to the general path.
         const uint32_t D = x - tab_cand;
-        const bool simple = M == (1u << lane) && m_tab >= 4u && D >= 32u && D <= 0xFFFEu && size > 21u && x + 16u < size - 5u;
+        // Extension format: symbols are up to 64 bytes, so the pair start is up to 64 bytes back and a 16-byte
+        // prefix may be the start of a longer match (:276-290), which the general path measures.
+        const bool simple = M == (1u << lane) && m_tab >= 4u && (!EXT || m_tab < 16u) && D >= (EXT ? 128u : 32u) && D <= 0xFFFEu &&
+                            size > 21u && x + 16u < size - 5u;
         const uint32_t simple_mask = __ballot_sync(FULL, simple);
         // The same for the hit that ENDS a literal scan: there the test uses the pair start from before the
         // pending literals are flushed (:80-100), up to 16 + 31 bytes back, hence the wider margin.
-        const uint32_t simple_scan_mask = __ballot_sync(FULL, simple && D >= 64u);
+        const uint32_t simple_scan_mask = __ballot_sync(FULL, simple && D >= (EXT ? 192u : 64u));
         // A lane is a CERTAIN MISS when its word differs from its candidate's and no other lane of the window
         // can change that candidate: the probe fails whatever the parse did (and the block does not end nearby).
         const uint32_t miss_mask = __ballot_sync(FULL, M == (1u << lane) && m_tab < 4u && size > 21u && x + 16u < size - 5u);
@@ -503,11 +507,17 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
             // ---------------- one match attempt at i == base + H against pos (:126-160)
             {
                 uint32_t k = __shfl_sync(FULL, m, H);                  // common prefix, capped at 16
-                if (__shfl_sync(FULL, (uint32_t)ovr, H)) {             // in-window candidate: compare now
-                    const uint32_t t = lane & 15u;
-                    const bool ne = __ldg(in + i + t) != __ldg(in + pos + t);
-                    const uint32_t nm = __ballot_sync(FULL, ne) | 0xFFFF0000u;
-                    k = (uint32_t)__ffs((int)nm) - 1u;
+                const bool in_window = __shfl_sync(FULL, (uint32_t)ovr, H) != 0;
+                if (in_window || (EXT && k == 16u)) {
+                    // compare now: an in-window candidate, or (extension format) a prefix that may run on to 64 bytes
+                    const uint32_t lim = EXT ? 64u : 16u;
+                    k = lim;
+                    for (uint32_t t0 = 0; t0 < lim; t0 += 32u) {
+                        const uint32_t t = t0 + lane;
+                        const bool ne = t < lim && __ldg(in + i + t) != __ldg(in + pos + t);
+                        const uint32_t nm = __ballot_sync(FULL, ne);
+                        if (nm) { k = t0 + (uint32_t)__ffs((int)nm) - 1u; break; }
+                    }
                 }
                 const uint32_t room = e.rep - pos;
                 if (k > room) k = room - 1u;                           // :139-141
@@ -516,10 +526,12 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
                     c = H + 1u;
                     continue;
                 }
-                i += k;                                                // :154
-                e.match(room, k, i);                                   // :152-159 (mlen[k] = k-1, 16 -> 15)
+                uint32_t nibble, adv;
+                match_code(k, nibble, adv);                            // mlen[] (:44-45): 4..16 -> k-1; 17..31 -> 16; 32 / 48 / 64 -> nibble 0 / 1 / 2
+                i += adv;                                              // :154 / :307
+                e.match(room, nibble, i);                              // :152-159
                 if (!(i < size) && !(i < size - 5u)) { done = true; break; }      // probe would be unobservable
-                c = H + k;
+                c = H + adv;
                 chain_pending = true;
             }
         }
@@ -540,7 +552,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
     return e.finish(flags);
 }
 
-template <bool FAT>
+template <bool FAT, bool EXT>
 __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
 {
     __shared__ WarpWs ws_all[kWarps];
@@ -560,7 +572,7 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
         const uint64_t at = b * (uint64_t)a.block;
         const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
         uint32_t flags;
-        const uint32_t c = encode_block_batch<FAT>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
+        const uint32_t c = encode_block_batch<FAT, EXT>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
         if (lane == 0) { a.sizes[b] = c; if (a.tailflags) a.tailflags[b] = flags; }
         __syncwarp();
     }
@@ -568,12 +580,17 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
 
 }  // namespace
 
-cudaError_t launch_encode_batch(const EncodeArgs& a, cudaStream_t st)
+cudaError_t launch_encode_batch(const EncodeArgs& a, bool ext, cudaStream_t st)
 {
     if (a.nb == 0) return cudaSuccess;
     const unsigned ctas = (a.n_slots + kWarps - 1) / kWarps;
-    if (a.fat) encode_batch_kernel<true><<<ctas, kWarps * 32, 0, st>>>(a);
-    else       encode_batch_kernel<false><<<ctas, kWarps * 32, 0, st>>>(a);
+    if (ext) {
+        if (a.fat) encode_batch_kernel<true, true><<<ctas, kWarps * 32, 0, st>>>(a);
+        else       encode_batch_kernel<false, true><<<ctas, kWarps * 32, 0, st>>>(a);
+    } else {
+        if (a.fat) encode_batch_kernel<true, false><<<ctas, kWarps * 32, 0, st>>>(a);
+        else       encode_batch_kernel<false, false><<<ctas, kWarps * 32, 0, st>>>(a);
+    }
     return cudaGetLastError();
 }
 
