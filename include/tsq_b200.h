@@ -197,6 +197,24 @@ bool tsqDecompress_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_
 
 #ifdef __cplusplus
 }
+
+/* turbosqueeze.h:543-544,615-616 -- the asynchronous job API.  As in the reference these two have C linkage but
+ * C++ parameter types.  Jobs of one context run in submission order on the context's job thread (the reference's
+ * writer thread, tsq_threads.cpp:192-275, is where its callbacks run too): progress_cb(id, 1.0) then
+ * completion_cb(id, success).  Returns the job id (>= 1); on an early failure completion_cb(0, false) is invoked
+ * and 0 returned (tsq_threads.cpp:296-306).  Callbacks may submit jobs to another context (test/test.cpp:247-262).
+ * tsqDeallocateContext*_MT waits for the jobs in flight (tsq_context.cpp:150-155). */
+#include <functional>
+extern "C" {
+uint32_t tsqCompressAsync_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
+                             bool outfile, bool useextensions, uint32_t level,
+                             std::function<void(uint32_t jobid, bool)> user_completion_cb,
+                             std::function<void(uint32_t jobid, double)> user_progress_cb);                     /* :543 */
+uint32_t tsqDecompressAsync_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out,
+                               size_t* szout, bool outfile,
+                               std::function<void(uint32_t jobid, bool)> user_completion_cb,
+                               std::function<void(uint32_t jobid, double)> user_progress_cb);                   /* :615 */
+}
 #endif
 
 #endif /* TSQ_B200_H */

@@ -252,6 +252,21 @@ def test_batch_encoder_table_formats_are_bit_exact(torch, ctx, checker, fat):
         ctx.set_option("encode_impl", 0)
 
 
+def test_cpp_caller_of_the_reference_api(torch, tmp_path):
+    """A C++ program written against the reference's API (block calls, buffer API, async jobs chained from
+    callbacks, drain on destroy, FILE* entry points -- modelled on the reference's test/test.cpp) links
+    libturbosqueeze_b200.so and passes."""
+    import subprocess
+    import turbosqueeze_b200 as T
+    root = os.path.dirname(HERE)
+    exe = str(tmp_path / "async_harness")
+    libdir = os.path.dirname(T.library_path())
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), os.path.join(HERE, "async_harness.cpp"),
+                    "-L" + libdir, "-lturbosqueeze_b200", "-Wl,-rpath," + libdir, "-lpthread", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "async_harness ok" in r.stdout, (r.returncode, r.stdout[-500:], r.stderr[-1500:])
+
+
 def test_pipelined_host_path_equals_one_shot(torch, ctx):
     """The chunked, stream-overlapped host path (H2D | kernels | D2H) must produce the very same container
     as one-shot staging, including the bytes a chunk's last block reads from the next chunk."""

@@ -8,7 +8,11 @@
 #include "tsq_device.cuh"
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdarg>
+#include <deque>
+#include <functional>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -738,20 +742,64 @@ extern "C" void tsqDecompress(FILE* in, FILE* out)
     free(blob);
 }
 
-// ---- synchronous buffer API (tsq_threads.cpp:413-441, :862-890)
-struct TSQCompressionContext_MT   { tsqb_context* dev; bool verbose; };
-struct TSQDecompressionContext_MT { tsqb_context* dev; bool verbose; };
+// ---- buffer API (tsq_threads.cpp:278-441, :679-890)
+// The reference's contexts are thread pools; here a context is a device context plus ONE job thread that runs
+// the queued jobs in order and invokes their callbacks (the reference's callbacks run on its writer thread).
+namespace {
+struct JobThread {
+    std::mutex m;
+    std::condition_variable cv;
+    std::deque<std::function<void()>> jobs;
+    bool stop = false;
+    uint32_t next_id = 1;
+    std::thread th;
+    JobThread() : th([this] { run(); }) {}
+    ~JobThread()                                                     // drains: tsq_context.cpp:150-155 waits for in-flight jobs
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv.notify_all();
+        th.join();
+    }
+    uint32_t submit(std::function<void(uint32_t)> job)
+    {
+        std::lock_guard<std::mutex> lk(m);
+        const uint32_t id = next_id++;
+        if (next_id == 0) next_id = 1;
+        jobs.emplace_back([job, id] { job(id); });
+        cv.notify_one();
+        return id;
+    }
+    void run()
+    {
+        for (;;) {
+            std::function<void()> j;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [this] { return stop || !jobs.empty(); });
+                if (jobs.empty()) return;                            // stop requested and nothing left
+                j = std::move(jobs.front());
+                jobs.pop_front();
+            }
+            j();
+        }
+    }
+};
+}  // namespace
+
+struct TSQCompressionContext_MT   { tsqb_context* dev; bool verbose; JobThread* jobs; };
+struct TSQDecompressionContext_MT { tsqb_context* dev; bool verbose; JobThread* jobs; };
 
 extern "C" struct TSQCompressionContext_MT* tsqAllocateContextCompression_MT(bool verbose)
 {
     tsqb_context* d = nullptr;
     if (tsqb_create(&d, 0) != 0) { if (verbose) printf("Error: %s\n", tsqb_last_error()); return nullptr; }
-    return new TSQCompressionContext_MT{d, verbose};
+    return new TSQCompressionContext_MT{d, verbose, new JobThread()};
 }
 
 extern "C" void tsqDeallocateContextCompression_MT(struct TSQCompressionContext_MT* ctx)
 {
     if (!ctx) return;
+    delete ctx->jobs;                                                // waits for the queued jobs
     tsqb_destroy(ctx->dev);
     delete ctx;
 }
@@ -760,12 +808,13 @@ extern "C" struct TSQDecompressionContext_MT* tsqAllocateContextDecompression_MT
 {
     tsqb_context* d = nullptr;
     if (tsqb_create(&d, 0) != 0) { if (verbose) printf("Error: %s\n", tsqb_last_error()); return nullptr; }
-    return new TSQDecompressionContext_MT{d, verbose};
+    return new TSQDecompressionContext_MT{d, verbose, new JobThread()};
 }
 
 extern "C" void tsqDeallocateContextDecompression_MT(struct TSQDecompressionContext_MT* ctx)
 {
     if (!ctx) return;
+    delete ctx->jobs;
     tsqb_destroy(ctx->dev);
     delete ctx;
 }
@@ -822,4 +871,37 @@ extern "C" bool tsqDecompress_MT(struct TSQDecompressionContext_MT* ctx, uint8_t
         return false;
     }
     return store_output(blob, bn, out, szout, outfile, ctx->verbose);
+}
+
+// ---- asynchronous job API (tsq_threads.cpp:278-410, :679-859)
+extern "C" uint32_t tsqCompressAsync_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out,
+                                        size_t* szout, bool outfile, bool useextensions, uint32_t level,
+                                        std::function<void(uint32_t, bool)> completion_cb, std::function<void(uint32_t, double)> progress_cb)
+{
+    if (!ctx || !in || (!infile && szin == 0) || !out || !szout) {    // early failure: completion(0, false), id 0 (:296-306)
+        if (completion_cb) completion_cb(0, false);
+        return 0;
+    }
+    return ctx->jobs->submit([=](uint32_t id) {
+        const bool ok = tsqCompress_MT(ctx, in, szin ? szin : 1, infile, out, szout, outfile, useextensions, level);
+        if (ctx->verbose) printf("Compression job %u %s\n", id, ok ? "done" : "failed");
+        if (ok && progress_cb) progress_cb(id, 1.0);
+        if (completion_cb) completion_cb(id, ok);
+    });
+}
+
+extern "C" uint32_t tsqDecompressAsync_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out,
+                                          size_t* szout, bool outfile, std::function<void(uint32_t, bool)> completion_cb,
+                                          std::function<void(uint32_t, double)> progress_cb)
+{
+    if (!ctx || !in || (!infile && szin == 0) || !out || !szout) {
+        if (completion_cb) completion_cb(0, false);
+        return 0;
+    }
+    return ctx->jobs->submit([=](uint32_t id) {
+        const bool ok = tsqDecompress_MT(ctx, in, szin ? szin : 1, infile, out, szout, outfile);
+        if (ctx->verbose) printf("Decompression job %u %s\n", id, ok ? "done" : "failed");
+        if (ok && progress_cb) progress_cb(id, 1.0);
+        if (completion_cb) completion_cb(id, ok);
+    });
 }
