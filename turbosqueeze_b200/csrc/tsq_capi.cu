@@ -172,7 +172,7 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
 // `tables` (optional): caller-provided region of encode_slots_for(...) tables, for launches that overlap in time
 static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t total, uint32_t block, uint8_t* d_slots,
                               uint64_t stride, uint32_t* d_sizes, uint32_t* d_tailflags, uint32_t with_ext, void* stream,
-                              uint16_t* tables = nullptr)
+                              uint16_t* tables = nullptr, int64_t slot_cap = 0)
 {
     if (!c) return fail("tsqb_encode_blocks: null context");
     if (block == 0 || block > kBlockMax) return fail("tsqb_encode_blocks: block size %u not in 1..%u", block, kBlockMax);
@@ -185,7 +185,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
     a.epoch = (++c->launch_id) << 20;                                 // + the slot's block counter, < 2^20
     const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
-    a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, c->encode_slots);
+    a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, slot_cap > 0 ? slot_cap : c->encode_slots);
     a.fat = (c->encode_fat < 0 ? encode_wants_fat(impl, a.n_slots) : (impl == 3 && c->encode_fat != 0)) ? 1u : 0u;
     if (tables) { a.tables = tables; a.fat = impl == 3 ? 1u : 0u; }            // the pipelined path provisions sector tables
     else {
@@ -351,10 +351,12 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     const uint64_t per = (nb + K - 1) / K;                                   // blocks per chunk
     const int nchunks = (int)((nb + per - 1) / per);
     const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
+    // the chunks' kernels share the GPU: together they get the tables of one full grid (32 warps per SM)
+    const int64_t slot_cap = c->encode_slots > 0 ? c->encode_slots : ((int64_t)c->sm_count * 32 + nchunks - 1) / nchunks;
     uint64_t slots_tab[K], tab_at[K], tab_total = 0;
     for (int k = 0; k < nchunks; k++) {
         const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
-        slots_tab[k] = encode_slots_for(impl, b1 - b0, c->sm_count, c->encode_slots);
+        slots_tab[k] = encode_slots_for(impl, b1 - b0, c->sm_count, slot_cap);
         tab_at[k] = tab_total; tab_total += slots_tab[k];
     }
     const uint64_t ccap = 16 + per * (stride + 3) + 256;                     // container capacity of one chunk
@@ -376,7 +378,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
         CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
         // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
         if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
-                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)))) return 1;
+                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)), slot_cap)) return 1;
         uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
         uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
         CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,
