@@ -500,11 +500,17 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                     const uint32_t pl = (uint32_t)__ffs((int)pm) - 1u;
                     const uint32_t s_q = __shfl_sync(FULL, q, pl), s_src = __shfl_sync(FULL, srcq, pl), s_len = __shfl_sync(FULL, len, pl);
                     const bool s_far = EXT && s_src + OUT_RING < J1 + 16u;        // only long matches can be far here
-                    for (uint32_t t = lane; t < s_len; t += 32u) {     // one trip without extensions (s_len <= 16)
+                    if constexpr (EXT) {
+                        for (uint32_t t = lane; t < s_len; t += 32u) {
+                            uint32_t byte;
+                            if (s_far) byte = __ldcg(o_al + s_src + t);
+                            else asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + t) & kOMask)) : "memory");
+                            asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + t) & kOMask)), "r"(byte) : "memory");
+                        }
+                    } else if (lane < s_len) {
                         uint32_t byte;
-                        if (EXT && s_far) byte = __ldcg(o_al + s_src + t);
-                        else asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + t) & kOMask)) : "memory");
-                        asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + t) & kOMask)), "r"(byte) : "memory");
+                        asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + lane) & kOMask)) : "memory");
+                        asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + lane) & kOMask)), "r"(byte) : "memory");
                     }
                     pm &= pm - 1u;
                 }
