@@ -97,8 +97,9 @@ int tsqb_encode_blocks(tsqb_context* ctx, const uint8_t* d_in, uint64_t total, u
  * :137-314).  Stream b starts at d_comp + (d_offsets ? d_offsets[b] : b * slot_stride); its decoded
  * bytes go to d_out + b * out_stride (never more than out_stride bytes, never past the header
  * size: unlike the reference nothing is written beyond the decoded size).
- *   d_comp_sizes  optional (may be NULL): readable bytes of each stream, used only to stop a corrupt
- *                 stream from walking off its buffer (the reference ignores inputSize)
+ *   d_comp_sizes  readable bytes of each stream: bounds the staging look-ahead and stops a corrupt stream from
+ *                 walking off its buffer (the reference ignores inputSize).  May be NULL only with d_offsets ==
+ *                 NULL (then slot_stride bounds every stream)
  *   d_out_sizes   n_blocks x u32: decoded size, 0 when the header exceeds 4 MiB (tsq_decode.cpp:53)
  *                 or out_stride
  */

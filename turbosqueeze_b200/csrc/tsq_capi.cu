@@ -210,6 +210,8 @@ extern "C" int tsqb_decode_blocks(tsqb_context* c, const uint8_t* d_comp, const 
 {
     if (!c) return fail("tsqb_decode_blocks: null context");
     if (nb == 0) return 0;
+    // packed streams have no slot to bound a corrupt stream (or the staging look-ahead): their sizes are required
+    if (d_offsets && !d_comp_sizes) return fail("tsqb_decode_blocks: d_comp_sizes is required together with d_offsets");
     CU(cudaSetDevice(c->device));
     DecodeArgs a;
     a.comp = d_comp; a.offs = d_offsets; a.stride = stride; a.csizes = d_comp_sizes; a.nb = nb;
@@ -389,20 +391,28 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     }
     // results leave in order; the body of chunk k goes behind the bodies before it
     uint8_t* host = host_out;
+    if (!host) {                                                              // malloc mode: the size is known last -> worst case
+        host = (uint8_t*)malloc(16 + nb * (stride + 3));
+        if (!host) return fail("compress: malloc failed");
+    }
     uint64_t at = 16;
-    for (int k = 0; k < nchunks; k++) {
-        CU(cudaEventSynchronize(c->ev_done[k]));
+    cudaError_t err = cudaSuccess;
+    bool too_small = false;
+    for (int k = 0; k < nchunks && err == cudaSuccess && !too_small; k++) {
+        err = cudaEventSynchronize(c->ev_done[k]);
+        if (err != cudaSuccess) break;
         const uint64_t body = c->h_len[k] - 16;
-        if (!host) {                                                          // malloc mode: size known only now -> worst case
-            host = (uint8_t*)malloc(16 + nb * (stride + 3));
-            if (!host) return fail("compress: malloc failed");
-        } else if (host_out && at + body > host_cap) {
-            return fail("compress: output needs more than the %llu bytes the caller gave", (unsigned long long)host_cap);
-        }
-        CU(cudaMemcpyAsync(host + at, (uint8_t*)c->cont.p + (uint64_t)k * ccap + 16, body, cudaMemcpyDeviceToHost, c->s_out));
+        if (host_out && at + body > host_cap) { too_small = true; break; }
+        err = cudaMemcpyAsync(host + at, (uint8_t*)c->cont.p + (uint64_t)k * ccap + 16, body, cudaMemcpyDeviceToHost, c->s_out);
         at += body;
     }
-    CU(cudaStreamSynchronize(c->s_out));
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->s_out);
+    if (err != cudaSuccess || too_small) {
+        cudaDeviceSynchronize();                                              // let the other chunks finish before the buffers are reused
+        if (!host_out) free(host);
+        if (too_small) return fail("compress: output needs more than the %llu bytes the caller gave", (unsigned long long)host_cap);
+        return fail("compress: %s", cudaGetErrorString(err));
+    }
     memcpy(host, "TSQ1", 4);                                                  // turbosqueeze.cpp:64-67
     const uint32_t nb32 = (uint32_t)nb;
     memcpy(host + 4, &nb32, 4);
