@@ -93,7 +93,8 @@ int tsqb_encode_blocks(tsqb_context* ctx, const uint8_t* d_in, uint64_t total, u
                        void* stream);
 
 /*
- * Decode n_blocks streams.  Replaces, per block, tsqDecode (tsq_decode.cpp:129-135 -> :42-126 /
+ * Decode n_blocks streams (d_comp must stay readable for 16 bytes behind the last stream: it is staged in
+ * 16-byte units).  Replaces, per block, tsqDecode (tsq_decode.cpp:129-135 -> :42-126 /
  * :137-314).  Stream b starts at d_comp + (d_offsets ? d_offsets[b] : b * slot_stride); its decoded
  * bytes go to d_out + b * out_stride (never more than out_stride bytes, never past the header
  * size: unlike the reference nothing is written beyond the decoded size).

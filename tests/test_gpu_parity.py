@@ -158,6 +158,35 @@ def test_decode_restores_input(torch, ctx, oracle, lanes, ext):
         ctx.set_option("decode_lanes", 0)
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("ext", [0, 1])
+def test_decode_of_garbage_streams_terminates(torch, ctx, ext):
+    """The reference does not validate streams (tsq_decode.cpp:42-126 reads whatever the bytes say).  The device
+    decoder must at least stay inside its buffers and terminate: random bytes behind a plausible header, truncated
+    real streams, and offsets pointing before the block."""
+    rng = np.random.default_rng(1234 + ext)
+    nb, block, stride = 96, 65536, 8192
+    comp = rng.integers(0, 256, size=nb * stride + 64, dtype=np.uint8)     # 16 readable bytes behind the last stream
+    for b in range(nb):
+        size = int(rng.integers(0, block + 1))
+        comp[b * stride: b * stride + 3] = [size & 0xFF, (size >> 8) & 0xFF, size >> 16]
+    sizes = rng.integers(0, stride, size=nb).astype(np.int32)
+    d_comp = torch.from_numpy(comp).cuda()
+    d_sizes = torch.from_numpy(sizes).cuda()
+    out, osz = ctx.decode_blocks(d_comp, nb, block, ext, stride=stride, comp_sizes=d_sizes)
+    torch.cuda.synchronize()
+    assert out.numel() == nb * block and int(osz.max().item()) <= block
+    # a real stream cut short
+    buf = W.fill("text", 200000, seed=3)
+    from oraclelib import Oracle
+    slots, csz, _ = Oracle().encode_blocks(buf, 200000, 65536, ext)
+    d = torch.from_numpy(slots).cuda()
+    cut = torch.from_numpy((csz // 2).astype(np.int32)).cuda()
+    out, osz = ctx.decode_blocks(d, len(csz), 65536, ext, comp_sizes=cut)
+    torch.cuda.synchronize()
+    assert int(osz.sum().item()) == 200000          # the header is reported as it is; the tail of each block is unspecified
+
+
 def test_decode_rejects_oversize_header(torch, ctx):
     """tsq_decode.cpp:53 -- header size > 4 MiB => outputSize 0 (and nothing written)."""
     import turbosqueeze_b200 as T
