@@ -585,9 +585,12 @@ cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cud
         if (sizeof(SlotSmem<8192>) * nslots <= budget)  return launch_split_t<8192, true>(a, nslots, ctas, st);
         return launch_split_t<4096, true>(a, nslots, ctas, st);
     }
-    if (sizeof(SlotSmem<16384>) * nslots <= budget) return launch_split_t<16384, false>(a, nslots, ctas, st);
-    if (sizeof(SlotSmem<8192>) * nslots <= budget)  return launch_split_t<8192, false>(a, nslots, ctas, st);
-    if (sizeof(SlotSmem<4096>) * nslots <= budget)  return launch_split_t<4096, false>(a, nslots, ctas, st);
+    // Measured (profiles/r01_experiments.md): a ring that fills all 227 KB leaves the SM without L1 and is ~20 % slower
+    // than a 2 KiB ring (3.73 vs 3.03 ms on the bench workload); 1 KiB is no faster.  Keep >= 43 KB for L1.
+    const size_t roomy = 184u * 1024u;
+    if (sizeof(SlotSmem<16384>) * nslots <= roomy) return launch_split_t<16384, false>(a, nslots, ctas, st);
+    if (sizeof(SlotSmem<8192>) * nslots <= roomy)  return launch_split_t<8192, false>(a, nslots, ctas, st);
+    if (sizeof(SlotSmem<4096>) * nslots <= roomy)  return launch_split_t<4096, false>(a, nslots, ctas, st);
     return launch_split_t<2048, false>(a, nslots, ctas, st);
 }
 
