@@ -44,7 +44,7 @@ constexpr uint32_t kQMask    = kQueue - 1;
 constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
 constexpr uint32_t kSteps    = kQueue / kPairs;      // steps the walker can be ahead
 constexpr uint32_t kLook     = 40;                   // stream bytes one pair can touch (1 + 1 + 16 + 16) + slack
-constexpr uint32_t kWalkers  = 4;                    // walker warps per CTA (one per warp scheduler), slots dealt round-robin
+constexpr uint32_t kWalkers  = 2;                    // walker warps per CTA, slots dealt round-robin (1 or 2: 2.91 ms, 4: 3.05, 6: 3.12)
 constexpr uint32_t kMaxSlots = 32 - kWalkers;       // copier warps per CTA (copiers + walkers <= 1024 threads)
 
 
