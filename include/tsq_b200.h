@@ -72,11 +72,15 @@ void tsqb_destroy(tsqb_context* ctx);
  * all-literal stream = 3 + size + ceil(size/16)*(1 + 1/8 + 1/2) (tsq_encode.cpp:53-61,88-95). */
 uint64_t tsqb_slot_stride(uint32_t block_size);
 
-/* Kernel selection knobs (for benchmarking / tests).  key: "encode_impl" (0 = auto, 1 = scalar
- * thread-per-block, 2 = warp-per-block byte emitter, 3 = warp-per-block token batches), "decode_lanes" (0 = auto, else 1,2,4,8,16,32 lanes per
- * block), "encode_slots" (0 = auto: concurrent hash tables), "encode_fat" (batch encoder table format: -1 = auto, 0 = u16 tables, 1 = 32-byte sector
- * entries), "pipeline" (1 = the host-buffer calls overlap
- * PCIe copies with kernels in chunks, 0 = one-shot staging), "pipeline_min" (bytes below which one-shot is used).  Returns 0 when the key is known. */
+/* Knobs for benchmarking / tests.  Returns 0 when the key is known.
+ *   "encode_impl"   0 = auto (token-batch kernel), 1 = scalar thread-per-block, 2 = round-1 v1 warp kernel (no-ext only),
+ *                   3 = warp-per-block token batches (tsq_encode_batch.cu)
+ *   "encode_slots"  0 = auto: hash tables (= blocks) in flight
+ *   "encode_fat"    table format of the batch encoder: -1 = auto, 0 = 2^17 x u16, 1 = 32-byte sector entries
+ *   "decode_lanes"  0 = auto (34), 34 = walker + copier kernel (tsq_decode_split.cu), 33 = v1 warp kernel (no-ext only),
+ *                   1,2,4,8,16,32 = sub-warp pair-step kernel with that many lanes per block
+ *   "pipeline"      1 = the host-buffer calls overlap PCIe copies with kernels in chunks, 0 = one-shot staging
+ *   "pipeline_min"  bytes below which the host-buffer calls stage in one shot */
 int tsqb_set_option(tsqb_context* ctx, const char* key, int64_t value);
 
 /*

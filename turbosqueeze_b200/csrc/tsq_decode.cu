@@ -1,4 +1,5 @@
-// tsq_decode.cu -- token-stream decoder for sm_100a.
+// tsq_decode.cu -- the sub-warp pair-step decoder (round-1 v1, kept as a cross-check; the production decoder is
+// tsq_decode_split.cu) and the decode dispatcher.
 //
 // Semantics: reference tsqDecodeNoext (tsq_decode.cpp:42-126) and the extension variant
 // (tsq_decode.cpp:137-314), restated around a "pair step": the reference's inner body handles one
@@ -141,7 +142,7 @@ static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream
 cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
 cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st);
 
-// lanes: 0 = auto; 34 = walker + copier kernel (tsq_decode_split.cu, the default without extensions);
+// lanes: 0 = auto; 34 = walker + copier kernel (tsq_decode_split.cu, the default, both formats);
 // 1..32 = sub-warp kernel with that many lanes per block; 33 = force the warp-per-block
 // step kernel (tsq_decode_warp.cu), 32 = force the pair-step kernel at full warp width
 cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st)

@@ -38,7 +38,7 @@ struct DecodeArgs {
 };
 
 // encode_impl: 1 = scalar (one thread per block), 2 = warp per block (byte-at-a-time emitter),
-// 3 = warp per block with token batches (tsq_encode_batch.cu, the default without extensions).
+// 3 = warp per block with token batches (tsq_encode_batch.cu, the default, both formats).
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int sm_count, cudaStream_t st);
 // bytes of one hash table of launch_encode(impl)
 uint32_t    encode_table_bytes(int impl, bool fat);
