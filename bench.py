@@ -267,9 +267,12 @@ def run_ours(args):
     gather = None
     if world > 1:
         from turbosqueeze_b200 import sharding as S
+        body_bytes = [0]
+
         def gather_step():
             cont, n = ctx.pack_container(slots, sizes, block, total)
             clen_local = int(n.item())
+            body_bytes[0] = clen_local - 16
             return S.gather_container(cont[:clen_local], total_all, nb * world, dst=0)
         gather_step()
         barrier()
@@ -280,8 +283,14 @@ def run_ours(args):
         barrier()
         tg = torch.tensor([g0.elapsed_time(g1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        tb = torch.tensor([float(body_bytes[0])], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         if rank == 0:
-            gather = {"ms": round(float(tg[0]), 3), "container_bytes": int(gathered.numel()),
+            hdr = bytes(gathered[:16].cpu().numpy())
+            gather_ok = (hdr[:4] == b"TSQ1" and int.from_bytes(hdr[4:8], "little") == nb * world and
+                         int.from_bytes(hdr[8:16], "little") == total_all and int(gathered.numel()) == 16 + int(tb[0]) and
+                         bool(torch.equal(gathered[16:16 + body_bytes[0]], ctx.pack_container(slots, sizes, block, total)[0][16:16 + body_bytes[0]])))
+            gather = {"ms": round(float(tg[0]), 3), "container_bytes": int(gathered.numel()), "ok": gather_ok,
                       "what": "tsqb_pack_container per rank + all_gather of byte counts + variable-length gather to rank 0 (NCCL)"}
 
     if rank == 0:
