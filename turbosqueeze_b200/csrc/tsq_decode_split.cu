@@ -19,10 +19,9 @@
 //   * decoded bytes go to a shared-memory OUTPUT ring first; near matches (distance < ring) read
 //     their source there (29-cycle LDS instead of an L2 round trip), far matches read HBM/L2 bytes
 //     that an earlier step flushed;
-//   * every symbol is stored as a blind 16-byte run in DESCENDING byte order: the garbage tail of
-//     symbol s lands on bytes owned by later symbols, and those write their own byte later in
-//     program order, so no per-byte predicate is needed (the reference uses the same blind copy,
-//     tsq_decode.cpp:74-85, serially);
+//   * every symbol stores exactly its own bytes: the 16 byte stores of a lane are predicated from a
+//     length mask (ptxas turns the mask into predicates with two R2P, so this costs the same as the
+//     reference's blind 16-byte copy, tsq_decode.cpp:74-85, and needs no ordering between lanes);
 //   * symbols whose source lies inside the output of the same step are copied afterwards, in position
 //     order, lane-per-byte with their exact length (sources always precede their own pair,
 //     tsq_encode.cpp:139-141, so everything such a symbol reads is in place when it is reached);
@@ -289,24 +288,26 @@ __device__ __forceinline__ void load16_smem(uint32_t base, uint32_t mask, uint32
     for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
 }
 
-// blind 16-byte store, highest byte first (see the header comment).  `wrap` must be warp-uniform:
-// the ordering argument needs every participating lane to execute the same store sequence in lockstep.
-// asm volatile: the compiler must keep the stores in exactly this order.
+// The bytes of one symbol into a ring: byte t is stored iff bit t of `lenmask` is set (ptxas materialises the mask
+// as predicates with two R2P, so exact lengths cost no more than a blind 16-byte run).  `wrap`: the run crosses the
+// end of the ring (per-lane; the fast path uses immediate offsets).
 template <int T>
-__device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4])
+__device__ __forceinline__ void store_bytes(uint32_t ad, const uint32_t v[4], uint32_t lenmask)
 {
-    asm volatile("st.volatile.shared.u8 [%0+%1], %2;" ::"r"(ad), "n"(T), "r"(v[T >> 2] >> (8 * (T & 3))) : "memory");
-    if constexpr (T > 0) store_bytes_desc<T - 1>(ad, v);
+    if (lenmask & (1u << T))
+        asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(ad), "n"(T), "r"(v[T >> 2] >> (8 * (T & 3))) : "memory");
+    if constexpr (T > 0) store_bytes<T - 1>(ad, v, lenmask);
 }
 
-__device__ __forceinline__ void store16_desc(uint32_t base, uint32_t mask, uint32_t q, const uint32_t v[4], bool wrap)
+__device__ __forceinline__ void store16(uint32_t base, uint32_t mask, uint32_t q, const uint32_t v[4], bool wrap, uint32_t lenmask)
 {
     if (!wrap) {
-        store_bytes_desc<15>(base + (q & mask), v);
+        store_bytes<15>(base + (q & mask), v, lenmask);
     } else {
 #pragma unroll
         for (int t = 15; t >= 0; t--)
-            asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(base + ((q + (uint32_t)t) & mask)), "r"(v[t >> 2] >> (8 * (t & 3))) : "memory");
+            if (lenmask & (1u << t))
+                asm volatile("st.shared.u8 [%0], %1;" ::"r"(base + ((q + (uint32_t)t) & mask)), "r"(v[t >> 2] >> (8 * (t & 3))) : "memory");
     }
 }
 
@@ -487,12 +488,9 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
                     }
                     placed = now;
                 }
-                const bool owrap = __any_sync(FULL, active && ((q & kOMask) + 16u > OUT_RING));
-                __syncwarp();                                                    // reconverge before the ordered stores
-                if (placed) store16_desc(obase, kOMask, q, v, owrap);
+                if (placed) store16(obase, kOMask, q, v, (q & kOMask) + 16u > OUT_RING, (1u << min(len, 16u)) - 1u);
                 // ---- symbols whose source lies inside this step's output: in position order, one at a time, the
-                // warp copying a symbol's bytes lane-per-byte with exact length (no garbage tail, so nothing placed
-                // before has to be repaired).  Sources always precede their own pair (tsq_encode.cpp:139-141), so by
+                // warp copying a symbol's bytes lane-per-byte.  Sources always precede their own pair (tsq_encode.cpp:139-141), so by
                 // the time a symbol is reached everything it reads is in place.
                 uint32_t pm = __ballot_sync(FULL, pending);
                 while (pm) {

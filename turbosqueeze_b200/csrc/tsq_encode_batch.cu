@@ -23,10 +23,9 @@
 //      pure function of the tokens -- symbol s of a batch that starts at byte Bj sits at
 //      Bj + (s/8 + 1) control bytes + (s/2 + 1) size bytes + the payload bytes before it
 //      (:57-61,94-95,157-159) -- so one warp prefix sum places all 32 payloads; control bytes are a
-//      ballot, size bytes a shuffle.  Payloads are staged in a shared-memory ring (literals as blind
-//      16-byte runs stored highest byte first, so a run's garbage tail is overwritten by the bytes
-//      that belong there, exactly what the reference's blind tsq_memcpy16 does serially, :88,108)
-//      and leave for HBM as coalesced 128-bit stores.
+//      ballot, size bytes a shuffle.  Payloads are staged in a shared-memory ring with exact-length
+//      byte stores (the reference copies a blind 16 bytes per literal run, :88,108, and lets the next
+//      symbol overwrite the tail) and leave for HBM as coalesced 128-bit stores.
 //   4. The inserts of the window are committed to the table (global memory, one table per block in
 //      flight) when the window is left.
 //
@@ -77,13 +76,14 @@ __device__ __forceinline__ uint32_t prefix16(const uint32_t a[4], const uint32_t
     return 16u;
 }
 
+// byte t of a payload is stored iff bit t of `lenmask` is set (a literal run of n bytes: n ones; a match offset: 2 ones);
+// ptxas materialises the mask as predicates with two R2P, so exact lengths cost no more than a blind 16-byte run
 template <int T>
-__device__ __forceinline__ void store_bytes_desc(uint32_t ad, const uint32_t v[4], bool lit)
+__device__ __forceinline__ void store_bytes(uint32_t ad, const uint32_t v[4], uint32_t lenmask)
 {
-    // bytes 2..15 only exist for literal runs; bytes 0..1 also carry a match offset
-    if (T < 2 || lit)
-        asm volatile("st.volatile.shared.u8 [%0+%1], %2;" ::"r"(ad), "n"(T), "r"(v[T >> 2] >> (8 * (T & 3))) : "memory");
-    if constexpr (T > 0) store_bytes_desc<T - 1>(ad, v, lit);
+    if (lenmask & (1u << T))
+        asm volatile("st.shared.u8 [%0+%1], %2;" ::"r"(ad), "n"(T), "r"(v[T >> 2] >> (8 * (T & 3))) : "memory");
+    if constexpr (T > 0) store_bytes<T - 1>(ad, v, lenmask);
 }
 
 // Table entry of this kernel.  The reference stores the low 16 bits of the position (tsq_encode.cpp:79);
@@ -225,18 +225,16 @@ struct BlockEncoder {
         const uint32_t pos = Bj + (lane >> 3) + 1u + (lane >> 1) + 1u + P;        // byte offset of this payload
         const uint32_t q = pos + oal;
 
-        // ---- payloads: literal run = blind 16 bytes, match = 2-byte offset (:152-153)
+        // ---- payloads: literal run = its 1..16 bytes (:88-91), match = 2-byte offset (:152-153)
         uint32_t v[4] = {tok & 0xFFFFu, 0, 0, 0};
         if (lit) ldg16(in + (tok & 0x3FFFFFu), v);
-        // the ordering argument needs all lanes in lockstep: one warp-uniform choice of the store path
-        const bool wrap = __any_sync(FULL, valid && ((q & kOMask) + 16u > kORing));
-        __syncwarp();
         if (valid) {
-            if (!wrap) store_bytes_desc<15>(obase + (q & kOMask), v, lit);
+            const uint32_t lenmask = (1u << pl) - 1u;
+            if ((q & kOMask) + 16u <= kORing) store_bytes<15>(obase + (q & kOMask), v, lenmask);
             else {
 #pragma unroll
                 for (int t = 15; t >= 0; t--)
-                    if (t < 2 || lit) ring_put(q + (uint32_t)t, v[t >> 2] >> (8 * (t & 3)));
+                    if (lenmask & (1u << t)) ring_put(q + (uint32_t)t, v[t >> 2] >> (8 * (t & 3)));
             }
         }
         // remember the last literal run for the never-initialised trailing bytes (finish)
@@ -248,7 +246,7 @@ struct BlockEncoder {
                 lit_src = __shfl_sync(FULL, tok & 0x3FFFFFu, L);
             }
         }
-        __syncwarp();                                                            // payloads (and their garbage tails) are down
+        __syncwarp();                                                            // payloads are down
         // ---- size bytes: one per pair, right before the pair's first payload (:95,159).  A trailing
         // odd symbol's byte is (nibble << 4) (:183-186).
         {
