@@ -261,6 +261,15 @@ def test_container_pack_index_and_buffer_api(torch, ctx, oracle):
         blob = T.tsq_compress_mt(buf[:n], 0)
         assert ref.decompress_mt(blob) == buf[:n].tobytes()           # the reference reads our container
         assert T.tsq_decompress_mt(ref.compress_mt(buf[:n], 1)) == buf[:n].tobytes()   # and we read its
+        # smaller container blocks (more blocks in flight) stay readable by the reference's decoder
+        L = T.library()
+        assert L.tsqb_set_container_block_size(262144) == 0
+        try:
+            small = T.tsq_compress_mt(buf[:n], 0)
+            assert int.from_bytes(small[4:8], "little") == (n + 262143) // 262144
+            assert ref.decompress_mt(small) == buf[:n].tobytes() and T.tsq_decompress_mt(small) == buf[:n].tobytes()
+        finally:
+            assert L.tsqb_set_container_block_size(1 << 22) == 0
 
 
 @pytest.mark.parametrize("fat", [0, 1], ids=["u16-tables", "sector-entries"])

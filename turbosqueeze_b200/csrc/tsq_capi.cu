@@ -604,6 +604,19 @@ extern "C" int tsqb_decompress_into(tsqb_context* c, const uint8_t* in, uint64_t
 }
 
 // ------------------------------------------------------------- layer 2: the reference's entry points
+// Block size of the container-producing entry points (tsqCompress, tsqCompress_MT, tsqCompressAsync_MT).  The
+// reference cuts 4 MiB blocks (turbosqueeze.h:37-38) and so does the default here, which makes the containers
+// identical; the container does not record the block size and the reference's decoder accepts any block <= 4 MiB
+// (tsq_decode.cpp:53), so a smaller block stays readable by `tsq d` while giving the GPU 16x more blocks in flight.
+static std::atomic<uint32_t> g_container_block{kBlockMax};
+
+extern "C" int tsqb_set_container_block_size(uint32_t block_size)
+{
+    if (block_size == 0 || block_size > kBlockMax) return fail("tsqb_set_container_block_size: %u not in 1..%u", block_size, kBlockMax);
+    g_container_block = block_size;
+    return 0;
+}
+
 static tsqb_context* g_default = nullptr;
 static std::mutex g_default_mtx;
 
@@ -730,7 +743,7 @@ extern "C" void tsqCompress(FILE* in, FILE* out, bool useextensions, uint32_t le
     std::vector<uint8_t> data;
     if (!read_all(in, data)) return;
     uint8_t* blob = nullptr; uint64_t n = 0;
-    if (tsqb_compress_buffer(c, data.data(), data.size(), kBlockMax, useextensions ? 1u : 0u, &blob, &n) != 0) {
+    if (tsqb_compress_buffer(c, data.data(), data.size(), g_container_block.load(), useextensions ? 1u : 0u, &blob, &n) != 0) {
         fprintf(stderr, "turbosqueeze_b200: tsqCompress failed: %s\n", tsqb_last_error());
         return;
     }
@@ -863,7 +876,7 @@ extern "C" bool tsqCompress_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in
     const uint8_t* p; size_t n;
     if (!load_input(in, szin, infile, store, &p, &n, ctx->verbose)) return false;
     uint8_t* blob = nullptr; uint64_t bn = 0;
-    if (tsqb_compress_buffer(ctx->dev, p, n, kBlockMax, useextensions ? 1u : 0u, &blob, &bn) != 0) {
+    if (tsqb_compress_buffer(ctx->dev, p, n, g_container_block.load(), useextensions ? 1u : 0u, &blob, &bn) != 0) {
         if (ctx->verbose) printf("Error: %s\n", tsqb_last_error());
         return false;
     }
