@@ -46,9 +46,15 @@ constexpr int      kWarps = 4;                       // warps (= blocks in fligh
 // token: bit 31 = literal, bits 27..30 = length - 1, low bits = literal source position / match offset
 constexpr uint32_t kTokLit = 0x80000000u;
 
+// "Was any entry of this group of 4 hashes written in this block?" -- one bit per 4 table entries, 4 KiB per warp.
+// A clear bit proves the entry is empty, so the probe needs no memory access at all (exact, never a guess): most
+// probes of small blocks and ~13 % of the probes of a 256 KiB text block.
+constexpr uint32_t kBloomWords = kHashSlots / 4u / 32u;
+
 struct __align__(16) WarpWs {
     uint8_t  oring[kORing];
     uint32_t tok[kTok];
+    uint32_t written[kBloomWords];
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -348,8 +354,8 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         const uint32_t M = __match_any_sync(FULL, h);
         uint32_t tab_cand, m_tab;
         if constexpr (FAT) {
-            uint4 A, B;
-            load_entry(table, h, A, B);
+            uint4 A = make_uint4(0, 0, 0, 0), B = A;                   // all-zero = an entry of no epoch
+            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, h, A, B);
             // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
             // (expand_pos(0, x)), one shared, cache-resident location.
             const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
@@ -539,7 +545,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         {
             const uint32_t mine = M & inP;
             if (((inP >> lane) & 1u) && (mine >> lane) == 1u) {
-                if constexpr (FAT) store_entry(table, h, x, own, epoch);
+                if constexpr (FAT) { store_entry(table, h, x, own, epoch); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
                 else table16[h] = (uint16_t)x;
             }
             __syncwarp();
@@ -561,7 +567,12 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
     uint8_t* table = reinterpret_cast<uint8_t*>(a.tables) + (size_t)slot * (FAT ? kFatTableBytes : kTableBytes);
     uint64_t epoch = a.epoch;
     for (uint64_t b = slot; b < a.nb; b += a.n_slots) {
-        if constexpr (FAT) epoch++;                                    // a fresh (empty) table: tsqInit (tsq_context.cpp:77-80)
+        if constexpr (FAT) {
+            epoch++;                                                   // a fresh (empty) table: tsqInit (tsq_context.cpp:77-80)
+            uint4* w4 = reinterpret_cast<uint4*>(ws.written);
+            for (uint32_t q = lane; q < kBloomWords / 4u; q += 32u) w4[q] = make_uint4(0, 0, 0, 0);
+            __syncwarp();
+        }
         else {
             uint4* t4 = reinterpret_cast<uint4*>(table);
             for (uint32_t q = lane; q < kTableBytes / 16u; q += 32u) t4[q] = make_uint4(0, 0, 0, 0);
