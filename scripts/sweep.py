@@ -21,6 +21,8 @@ def main():
     enc_slots = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0]
     dec_lanes = [int(x) for x in sys.argv[5].split(",")] if len(sys.argv) > 5 else [0]
     ctx = T.Context(0)
+    if os.environ.get("ENC_HINTS"):
+        ctx.set_option("encode_hints", int(os.environ["ENC_HINTS"]))
     if os.environ.get("L2_FETCH"):
         ctx.set_option("l2_fetch", int(os.environ["L2_FETCH"]))
     buf = W.fill(kind, n, seed=20240917)

@@ -279,7 +279,8 @@ def test_batch_encoder_table_formats_are_bit_exact(torch, ctx, checker, fat):
     ctx.set_option("encode_fat", fat)
     try:
         for kind, n, block in [("text", (3 << 20) + 777, 4096), ("text", (2 << 20) + 5, 262144), ("rep8", 1 << 20, 65536),
-                               ("random", (1 << 20) + 3, 16384), ("runs", 300000, 300000), ("text", 70000, 70000)]:
+                               ("random", (1 << 20) + 3, 16384), ("runs", 300000, 300000), ("text", 70000, 70000),
+                               ("text", (3 << 20) + 11, 1 << 20), ("text", (4 << 20) + 100, 1 << 22)]:   # entries aged by > 3 segments
             buf = make_input(kind, n, seed=n + 11)
             want_slots, want_sizes, _ = checker.encode_blocks(buf, n, block, 0)
             for rep in range(2):                                   # second pass: tables hold entries of older epochs

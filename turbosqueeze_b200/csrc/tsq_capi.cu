@@ -78,6 +78,7 @@ struct tsqb_context {
     int encode_impl = 0;       // 0 auto, 1 scalar, 2 warp
     int decode_lanes = 0;      // 0 auto
     int64_t encode_slots = 0;  // 0 auto
+    int encode_hints = 0;      // see EncodeArgs::hints
     int encode_fat = -1;       // batch encoder table format: -1 auto, 0 u16 tables, 1 sector entries
     DevBuf tables;             // hash tables of the blocks in flight (zeroed when allocated: epoch 0 = empty)
     DevBuf ftables;            // batch encoder: 32-byte entries, only ever written by that kernel, zeroed at allocation
@@ -86,7 +87,9 @@ struct tsqb_context {
     DevBuf in, slots, sizes, out, osizes, cont, offs, ext, misc;
     cudaStream_t stream = nullptr;
     // pipelined host path: copy-in / copy-out streams, one compute stream + events per chunk in flight
-    static constexpr int kPipe = 4;
+    static constexpr int kPipe = 16;           // most chunks a buffer is cut into
+    int pipe_taper = 0;                        // compress: chunks shrink towards the end (option "pipe_taper")
+    int pipe_chunks = 4;                       // chunks actually used (option "pipe_chunks", 1..kPipe)
     cudaStream_t s_in = nullptr, s_out = nullptr, s_chunk[kPipe] = {};
     cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
     uint64_t* h_len = nullptr;                 // pinned: per-chunk container length
@@ -159,8 +162,11 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
     if (!strcmp(key, "decode_lanes")) { c->decode_lanes = (int)v; return 0; }
     if (!strcmp(key, "encode_slots")) { c->encode_slots = v; return 0; }
     if (!strcmp(key, "encode_fat")) { c->encode_fat = (int)v; return 0; }
+    if (!strcmp(key, "encode_hints")) { c->encode_hints = (int)v; return 0; }
     if (!strcmp(key, "pipeline")) { c->pipeline = (int)v; return 0; }
     if (!strcmp(key, "pipeline_min")) { c->pipeline_min = (uint64_t)v; return 0; }
+    if (!strcmp(key, "pipe_taper")) { c->pipe_taper = (int)v; return 0; }
+    if (!strcmp(key, "pipe_chunks")) { if (v < 1 || v > tsqb_context::kPipe) return 1; c->pipe_chunks = (int)v; return 0; }
     if (!strcmp(key, "l2_fetch")) {                                  // 32 / 64 / 128: DRAM fetch granularity hint
         cudaSetDevice(c->device);
         return cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v) == cudaSuccess ? 0 : 1;
@@ -183,6 +189,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     EncodeArgs a;
     a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
+    a.hints = (uint32_t)c->encode_hints;
     a.epoch = (++c->launch_id) << 20;                                 // + the slot's block counter, < 2^20
     const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, slot_cap > 0 ? slot_cap : c->encode_slots);
@@ -348,28 +355,51 @@ static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, c
 static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
                               uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size)
 {
-    constexpr int K = tsqb_context::kPipe;
+    constexpr int KMAX = tsqb_context::kPipe;
+    const int K = c->pipe_chunks;
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
-    const uint64_t per = (nb + K - 1) / K;                                   // blocks per chunk
-    const int nchunks = (int)((nb + per - 1) / per);
+    // chunk boundaries (in blocks).  Equal chunks, or -- option "pipe_taper" -- chunks that shrink towards the end:
+    // a block takes ~20 ms from the arrival of its bytes however few blocks are in flight (its parse is a serial
+    // chain), so the job ends one block latency after the LAST chunk has landed; a small last chunk lands and
+    // leaves quickly.
+    uint64_t cb[KMAX + 1];
+    int nchunks = 0;
+    cb[0] = 0;
+    if (c->pipe_taper && K >= 3) {
+        double w[KMAX], sum = 0;
+        for (int k = 0; k < K; k++) { w[k] = 1.0 / (1.0 + 0.6 * k * k / (double)K); sum += w[k]; }
+        double acc = 0;
+        for (int k = 0; k < K; k++) {
+            acc += w[k];
+            uint64_t e = k == K - 1 ? nb : (uint64_t)(nb * (acc / sum) + 0.5);
+            if (e > nb) e = nb;
+            if (e > cb[nchunks]) cb[++nchunks] = e;
+        }
+    } else {
+        const uint64_t per = (nb + K - 1) / K;
+        for (uint64_t b = 0; b < nb; b += per) cb[++nchunks] = (b + per < nb) ? b + per : nb;
+    }
+    uint64_t per = 0;                                                         // blocks in the largest chunk
+    for (int k = 0; k < nchunks; k++) if (cb[k + 1] - cb[k] > per) per = cb[k + 1] - cb[k];
     const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
     // the chunks' kernels share the GPU: together they get the tables of one full grid (32 warps per SM)
-    const int64_t slot_cap = c->encode_slots > 0 ? c->encode_slots : ((int64_t)c->sm_count * 32 + nchunks - 1) / nchunks;
-    uint64_t slots_tab[K], tab_at[K], tab_total = 0;
+    // (each chunk its share, in proportion to its blocks)
+    int64_t slot_cap[KMAX];
+    uint64_t slots_tab[KMAX], tab_at[KMAX], tab_total = 0;
     for (int k = 0; k < nchunks; k++) {
-        const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
-        slots_tab[k] = encode_slots_for(impl, b1 - b0, c->sm_count, slot_cap);
+        slot_cap[k] = c->encode_slots > 0 ? c->encode_slots : (int64_t)(((uint64_t)c->sm_count * 32 * (cb[k + 1] - cb[k]) + nb - 1) / nb);
+        slots_tab[k] = encode_slots_for(impl, cb[k + 1] - cb[k], c->sm_count, slot_cap[k]);
         tab_at[k] = tab_total; tab_total += slots_tab[k];
     }
     const uint64_t ccap = 16 + per * (stride + 3) + 256;                     // container capacity of one chunk
     if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
-        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + K) * 8) || c->misc.ensure(64 * K) || (impl == 3 ? c->ftables : c->tables).ensure(tab_total * encode_table_bytes(impl, true)))
+        c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + KMAX) * 8) || c->misc.ensure(64 * KMAX) || (impl == 3 ? c->ftables : c->tables).ensure(tab_total * encode_table_bytes(impl, true)))
         return fail("compress: out of device memory");
     uint8_t* d_in = (uint8_t*)c->in.p;
     CU(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
     if (tail && tail_n) CU(cudaMemcpyAsync(d_in + total, tail, tail_n, cudaMemcpyHostToDevice, c->s_in));
     for (int k = 0; k < nchunks; k++) {
-        const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
+        const uint64_t b0 = cb[k], b1 = cb[k + 1];
         const uint64_t lo = b0 * block, hi = (b1 * block < total) ? b1 * block : total;
         // the last block of the chunk reads a few bytes past it (tsq_encode.cpp:74,126-128): ship them with this chunk
         const uint64_t hi_tail = (hi + TSQB_INPUT_PAD < total) ? hi + TSQB_INPUT_PAD : total;
@@ -380,7 +410,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
         CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
         // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
         if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
-                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)), slot_cap)) return 1;
+                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)), slot_cap[k])) return 1;
         uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
         uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
         CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,
@@ -429,7 +459,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
 static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* host_out, uint64_t host_cap,
                                 uint8_t** out, uint64_t* out_size)
 {
-    constexpr int K = tsqb_context::kPipe;
+    const int K = c->pipe_chunks;
     std::vector<uint64_t> offs;
     std::vector<uint32_t> sizes;
     uint32_t with_ext = 0, block = 0;

@@ -24,6 +24,7 @@ struct EncodeArgs {
     uint64_t       epoch;     // batch encoder: entries written under another epoch are empty (no per-block zeroing)
     uint32_t       fat;       // batch encoder: 1 = sector entries (kFatTableBytes per table), 0 = u16 tables
     uint32_t       n_slots;
+    uint32_t       hints = 0; // batch encoder experiments: 1 = table traffic evict-first in L2, 2 = streaming output stores
 };
 
 struct DecodeArgs {

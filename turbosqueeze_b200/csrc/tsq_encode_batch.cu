@@ -97,6 +97,11 @@ __device__ __forceinline__ void store_bytes(uint32_t ad, const uint32_t v[4], ui
 //   A.x  position (22 bits; its low 16 bits play the reference's role, so the candidate is the same)
 //        | low 10 bits of the tag;   A.y  high 5 bits of the tag;   A.z / B.z  epoch (low / high word)
 //   A.w, B.x, B.y  the 12 input bytes behind the hashed word
+//   A.y bits 5..19, B.w bits 0..14 / 15..29  ALIAS TAGS: the tags of the words 64 / 128 / 192 KiB behind the position.
+//        An entry older than 64 KiB names, through its low 16 bits, a position m x 64 KiB further on
+//        (tsq_encode.cpp:77-78); the probe hits only if the word THERE equals the probing word, which needs equal
+//        tags.  The committing lane reads those (sequential, cache-resident) words once, so a later probe of the
+//        aged entry is answered from the entry itself: unequal tags = certain miss, no second DRAM access.
 // * tag = word >> 17.  hash = (w ^ (w >> 12)) & 0x1FFFF determines bits 0..16 of w once bits 17..31 are known
 //   (b_i = h_i ^ b_{i+12} downwards), so "same slot and same tag" is EXACTLY "same 4-byte word": the hit test of
 //   :100 and the match length (:126-137) need no access to the candidate's bytes -- the second, dependent DRAM
@@ -106,17 +111,34 @@ __device__ __forceinline__ void store_bytes(uint32_t ad, const uint32_t v[4], ui
 // * a commit writes the whole sector, so DRAM needs no read-modify-write for it.
 // Blackwell has 256-bit global loads / stores (SASS LDG.E.ENL2.256 / STG.E.ENL2.256): one request per probe,
 // and a commit that covers its whole sector.
-__device__ __forceinline__ void load_entry(const uint4* table, uint32_t h, uint4& A, uint4& B)
+__device__ __forceinline__ void load_entry(const uint4* table, uint32_t h, uint4& A, uint4& B, uint64_t pol)
 {
-    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h) : "memory");
+    if (pol)
+        asm volatile("ld.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+                     : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h), "l"(pol) : "memory");
+    else
+        asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h) : "memory");
 }
 
-__device__ __forceinline__ void store_entry(uint4* table, uint32_t h, uint32_t pos, const uint32_t own[4], uint64_t epoch)
+// tag (word >> 17) of the 4-byte word at in[pos]: bits 17..31 live in bytes 2 and 3
+__device__ __forceinline__ uint32_t tag_at(const uint8_t* __restrict__ in, uint32_t pos)
+{
+    return ((uint32_t)__ldg(in + pos + 3u) << 7) | ((uint32_t)__ldg(in + pos + 2u) >> 1);
+}
+
+// a1..a3: alias tags, i.e. tag_at(pos + 64 KiB * {1, 2, 3}) where that position lies inside the block (a candidate
+// always precedes the probing position, so no other alias can ever be asked for).
+__device__ __forceinline__ void store_entry(uint4* table, uint32_t h, uint32_t pos, const uint32_t own[4], uint64_t epoch,
+                                            uint32_t a1, uint32_t a2, uint32_t a3, uint64_t pol)
 {
     const uint32_t tag = own[0] >> 17;
-    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(table + 2u * h), "r"(pos | (tag << 22)), "r"(tag >> 10),
-                 "r"((uint32_t)epoch), "r"(own[1]), "r"(own[2]), "r"(own[3]), "r"((uint32_t)(epoch >> 32)), "r"(0u) : "memory");
+    if (pol)
+        asm volatile("st.global.L2::cache_hint.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8}, %9;" ::"l"(table + 2u * h), "r"(pos | (tag << 22)), "r"((tag >> 10) | (a1 << 5)),
+                     "r"((uint32_t)epoch), "r"(own[1]), "r"(own[2]), "r"(own[3]), "r"((uint32_t)(epoch >> 32)), "r"(a2 | (a3 << 15)), "l"(pol) : "memory");
+    else
+        asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(table + 2u * h), "r"(pos | (tag << 22)), "r"((tag >> 10) | (a1 << 5)),
+                     "r"((uint32_t)epoch), "r"(own[1]), "r"(own[2]), "r"(own[3]), "r"((uint32_t)(epoch >> 32)), "r"(a2 | (a3 << 15)) : "memory");
 }
 
 __device__ __forceinline__ uint32_t lanes_from_to(uint32_t lo, uint32_t hi)   // bits lo..hi inclusive
@@ -140,6 +162,7 @@ struct BlockEncoder {
     uint32_t  Bj;             // byte offset of the control byte of the next batch's first group
     uint32_t  F;              // flushed up to here (q coordinates)
     uint32_t  lit_js, lit_src;// output offset / input position of the last literal run (0x80000000: none)
+    bool      stream_out;     // experiment: flushed output leaves with st.global.cs
 
     __device__ __forceinline__ void push(uint32_t tok)
     {
@@ -198,7 +221,8 @@ struct BlockEncoder {
         for (uint32_t at = F + 16u * lane; at < Ev; at += 512u) {
             uint4 x;
             asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)) : "memory");
-            *reinterpret_cast<uint4*>(o_al + at) = x;
+            if (stream_out) __stcs(reinterpret_cast<uint4*>(o_al + at), x);
+            else *reinterpret_cast<uint4*>(o_al + at) = x;
         }
         if (Ev > F) F = Ev;
         if (F < E) {                                                             // final tail
@@ -325,9 +349,12 @@ struct BlockEncoder {
 // hundred blocks in flight, whose tables (256 KiB each) and 64 KiB back-windows stay resident in the 126 MB L2.
 template <bool FAT, bool EXT>
 __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
-                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags)
+                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags, const uint32_t hints)
 {
+    uint64_t pol = 0;                                                  // experiment: table traffic marked evict-first in L2
+    if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     BlockEncoder e;
+    e.stream_out = (hints & 2u) != 0;
     e.in = in; e.size = size; e.lane = lane;
     e.oal = (uint32_t)(reinterpret_cast<uintptr_t>(out) & 15u);
     e.o_al = out - e.oal;
@@ -351,11 +378,19 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         ldg16(in + x, own);
         const uint32_t w = own[0];
         const uint32_t h = hash17(w);
+        // alias tags for this position's own entry, should it be committed: loaded now, with everything else of the
+        // window (sequential streams 64 / 128 / 192 KiB ahead of the scan), so that the commit waits for nothing
+        uint32_t a1 = 0, a2 = 0, a3 = 0;
+        if constexpr (FAT) {
+            if (x + 65536u < size)  a1 = tag_at(in, x + 65536u);
+            if (x + 131072u < size) a2 = tag_at(in, x + 131072u);
+            if (x + 196608u < size) a3 = tag_at(in, x + 196608u);
+        }
         const uint32_t M = __match_any_sync(FULL, h);
         uint32_t tab_cand, m_tab;
         if constexpr (FAT) {
             uint4 A = make_uint4(0, 0, 0, 0), B = A;                   // all-zero = an entry of no epoch
-            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, h, A, B);
+            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, h, A, B, pol);
             // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
             // (expand_pos(0, x)), one shared, cache-resident location.
             const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
@@ -363,17 +398,40 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
             tab_cand = expand_pos(p22 & 0xFFFFu, x);
             if (live && tab_cand == p22) {
                 // the entry really describes in[tab_cand]: same hash and same high word bits <=> same word (:100)
-                const uint32_t tag = (A.x >> 22) | (A.y << 10);
+                const uint32_t tag = ((A.x >> 22) | (A.y << 10)) & 0x7FFFu;
                 cb[0] = own[0]; cb[1] = A.w; cb[2] = B.x; cb[3] = B.y;
                 m_tab = tag == (w >> 17) ? prefix16(own, cb) : 0u;
             } else {                                                   // empty entry, or one older than 64 KiB (aliased)
-                ldg16(in + tab_cand, cb);
-                m_tab = prefix16(own, cb);                             // >= 4  <=>  the 4-byte words are equal (:100)
+                // aliased by 1..3 segments: the entry carries the tag of the word at the aliased position
+                const uint32_t seg = live ? (tab_cand - p22) >> 16 : 0u;
+                const uint32_t atag = seg == 1u ? (A.y >> 5) : (seg == 2u ? B.w : (B.w >> 15));
+                if (seg - 1u < 3u && (atag & 0x7FFFu) != (w >> 17)) m_tab = 0u;   // different words: the probe fails (:100)
+                else {
+                    ldg16(in + tab_cand, cb);
+                    m_tab = prefix16(own, cb);                         // >= 4  <=>  the 4-byte words are equal (:100)
+                }
             }
         } else {
             tab_cand = expand_pos(table16[h], x);                      // :76-78
             ldg16(in + tab_cand, cb);
             m_tab = prefix16(own, cb);
+        }
+        // ---- experiments (hints): warm the L2 for the windows to come while this window's loads are in flight
+        if (hints & 4u) {                                              // the input line ~6 windows ahead (first touch = DRAM)
+            if (lane == 0 && base + 192u < size) asm volatile("prefetch.global.L2 [%0];" ::"l"(in + base + 192u));
+        }
+        if constexpr (FAT) {
+            if (hints & 8u) {                                          // table sectors of the next window (it starts 32..48 positions on)
+                const uint32_t xn = x + 32u;
+                if (xn < size) {
+                    const uint32_t hn = hash17(ld_le32(in + xn));
+                    if ((ws.written[hn >> 7] >> ((hn >> 2) & 31u)) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + 2u * hn));
+                }
+                if (lane < 16u && xn + 32u < size) {
+                    const uint32_t hn = hash17(ld_le32(in + xn + 32u));
+                    if ((ws.written[hn >> 7] >> ((hn >> 2) & 31u)) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + 2u * hn));
+                }
+            }
         }
         const bool anydup = __any_sync(FULL, M != (1u << lane));
         uint32_t inP = 0, c = 0;
@@ -545,7 +603,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         {
             const uint32_t mine = M & inP;
             if (((inP >> lane) & 1u) && (mine >> lane) == 1u) {
-                if constexpr (FAT) { store_entry(table, h, x, own, epoch); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
+                if constexpr (FAT) { store_entry(table, h, x, own, epoch, a1, a2, a3, pol); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
                 else table16[h] = (uint16_t)x;
             }
             __syncwarp();
@@ -581,7 +639,7 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
         const uint64_t at = b * (uint64_t)a.block;
         const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
         uint32_t flags;
-        const uint32_t c = encode_block_batch<FAT, EXT>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags);
+        const uint32_t c = encode_block_batch<FAT, EXT>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags, a.hints);
         if (lane == 0) { a.sizes[b] = c; if (a.tailflags) a.tailflags[b] = flags; }
         __syncwarp();
     }
