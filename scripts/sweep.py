@@ -37,7 +37,9 @@ def main():
     for s in enc_slots:
         ctx.set_option("encode_slots", s)
         t = timeit(lambda: ctx.encode_blocks(d, n, block, 0, slots=slots, sizes=sizes), reps=2)
-        print(f"{kind} {block} nb={nb} encode slots={s}: {t:.3f} ms {n/t/1e6:.1f} GB/s ratio={int(sizes.sum().item())/n:.4f}", flush=True)
+        # checksum of every stream byte (slots are zero outside the streams): equal checksums <=> equal output for A/B runs
+        chk = int(slots.view(torch.int64).sum().item()) & 0xFFFFFFFFFFFF
+        print(f"{kind} {block} nb={nb} encode slots={s}: {t:.3f} ms {n/t/1e6:.1f} GB/s ratio={int(sizes.sum().item())/n:.4f} chk={chk:012x}", flush=True)
     ctx.set_option("encode_slots", 0)
     for lanes in dec_lanes:
         ctx.set_option("decode_lanes", lanes)

@@ -25,7 +25,8 @@ class TsqError(RuntimeError):
 
 
 def library_path():
-    return os.path.join(_HERE, "libturbosqueeze_b200.so")
+    # TSQB_LIBRARY: development only (scripts/build_variants.sh builds kernel variants for A/B timing)
+    return os.environ.get("TSQB_LIBRARY") or os.path.join(_HERE, "libturbosqueeze_b200.so")
 
 
 def library():

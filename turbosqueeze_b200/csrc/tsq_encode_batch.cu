@@ -41,7 +41,28 @@ constexpr unsigned FULL   = 0xffffffffu;
 constexpr uint32_t kTok   = 64;                      // token queue entries per warp
 constexpr uint32_t kORing = 1024;                    // output staging ring per warp (bytes)
 constexpr uint32_t kOMask = kORing - 1;
-constexpr int      kWarps = 4;                       // warps (= blocks in flight) per CTA
+#ifndef TSQB_ENC_WARPS
+#define TSQB_ENC_WARPS 4
+#endif
+constexpr int      kWarps = TSQB_ENC_WARPS;          // warps (= blocks in flight) per CTA
+
+// Development knobs (compile-time; scripts/build_variants.sh builds one library per combination, profiles/r01_experiments.md
+// records what they measured).  The defaults are the production kernel.
+#ifndef TSQB_ENC_FIXED_GRID
+#define TSQB_ENC_FIXED_GRID 0      // 1: windows on a fixed grid of 32 positions (1 + 32k) instead of starting at the next probe
+#endif
+#ifndef TSQB_ENC_PF_NEXT
+#define TSQB_ENC_PF_NEXT 0         // 1 (needs the fixed grid): L2 prefetch of the next window's table sectors before the decision loop
+#endif
+#ifndef TSQB_ENC_HINTS
+#define TSQB_ENC_HINTS 0           // 1: the run-time experiment hints (EncodeArgs::hints) are compiled in (costs 5 %)
+#endif
+#ifndef TSQB_ENC_DIAG
+#define TSQB_ENC_DIAG 0            // timing diagnostics, WRONG OUTPUT: 1 = table reads folded onto 256 sectors per block (L2-resident),
+#endif                             // 2 = commits not stored, 3 = both
+#ifndef TSQB_ENC_ALIAS8
+#define TSQB_ENC_ALIAS8 0          // 1: alias tags taken from the word's top byte only (one byte load instead of two)
+#endif
 
 // token: bit 31 = literal, bits 27..30 = length - 1, low bits = literal source position / match offset
 constexpr uint32_t kTokLit = 0x80000000u;
@@ -124,6 +145,9 @@ __device__ __forceinline__ void load_entry(const uint4* table, uint32_t h, uint4
 // tag (word >> 17) of the 4-byte word at in[pos]: bits 17..31 live in bytes 2 and 3
 __device__ __forceinline__ uint32_t tag_at(const uint8_t* __restrict__ in, uint32_t pos)
 {
+#if TSQB_ENC_ALIAS8
+    return (uint32_t)__ldg(in + pos + 3u) << 7;                      // top byte only: bits 7..14 of the tag
+#endif
     return ((uint32_t)__ldg(in + pos + 3u) << 7) | ((uint32_t)__ldg(in + pos + 2u) >> 1);
 }
 
@@ -349,8 +373,9 @@ struct BlockEncoder {
 // hundred blocks in flight, whose tables (256 KiB each) and 64 KiB back-windows stay resident in the 126 MB L2.
 template <bool FAT, bool EXT>
 __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
-                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags, const uint32_t hints)
+                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags, const uint32_t hints_)
 {
+    const uint32_t hints = TSQB_ENC_HINTS ? hints_ : 0u;
     uint64_t pol = 0;                                                  // experiment: table traffic marked evict-first in L2
     if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
     BlockEncoder e;
@@ -369,7 +394,8 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t i = 0, lit_from = 0;
     uint32_t base = 1;                // first probe is position 1 (:70-72)
-    bool chain_pending = false;       // lane 0 of the next window is a post-match probe (:162-170)
+    bool chain_pending = false;       // the next probe is a post-match probe (:162-170)
+    uint32_t c0 = 0;                  // lane of the window's first probe (fixed grid: the parse may enter a window anywhere)
 
     for (;;) {                                                         // one window per iteration
         // ---------------- window precompute (parallel over 32 positions)
@@ -390,7 +416,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         uint32_t tab_cand, m_tab;
         if constexpr (FAT) {
             uint4 A = make_uint4(0, 0, 0, 0), B = A;                   // all-zero = an entry of no epoch
-            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, h, A, B, pol);
+            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, (TSQB_ENC_DIAG & 1) ? (h & 255u) : h, A, B, pol);
             // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
             // (expand_pos(0, x)), one shared, cache-resident location.
             const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
@@ -405,7 +431,8 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
                 // aliased by 1..3 segments: the entry carries the tag of the word at the aliased position
                 const uint32_t seg = live ? (tab_cand - p22) >> 16 : 0u;
                 const uint32_t atag = seg == 1u ? (A.y >> 5) : (seg == 2u ? B.w : (B.w >> 15));
-                if (seg - 1u < 3u && (atag & 0x7FFFu) != (w >> 17)) m_tab = 0u;   // different words: the probe fails (:100)
+                constexpr uint32_t kAliasMask = TSQB_ENC_ALIAS8 ? 0x7F80u : 0x7FFFu;
+                if (seg - 1u < 3u && ((atag ^ (w >> 17)) & kAliasMask) != 0u) m_tab = 0u;   // different words: the probe fails (:100)
                 else {
                     ldg16(in + tab_cand, cb);
                     m_tab = prefix16(own, cb);                         // >= 4  <=>  the 4-byte words are equal (:100)
@@ -433,8 +460,18 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
                 }
             }
         }
+#if TSQB_ENC_FIXED_GRID && TSQB_ENC_PF_NEXT
+        if constexpr (FAT) {
+            // the next window is positions x + 32: its table sectors start their way from DRAM to L2 now and are read,
+            // after this window's commits, from L2
+            if (x + 32u < size) {
+                const uint32_t hn = hash17(ld_le32(in + x + 32u));
+                if ((ws.written[hn >> 7] >> ((hn >> 2) & 31u)) & 1u) asm volatile("prefetch.global.L2 [%0];" ::"l"(table + 2u * hn));
+            }
+        }
+#endif
         const bool anydup = __any_sync(FULL, M != (1u << lane));
-        uint32_t inP = 0, c = 0;
+        uint32_t inP = 0, c = c0;
         bool done = false;
 
         // A lane is a SIMPLE hit when its probe succeeds and yields the match (pos = tab_cand, k = m_tab)
@@ -603,12 +640,19 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         {
             const uint32_t mine = M & inP;
             if (((inP >> lane) & 1u) && (mine >> lane) == 1u) {
-                if constexpr (FAT) { store_entry(table, h, x, own, epoch, a1, a2, a3, pol); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
+                if constexpr (FAT) { if (!(TSQB_ENC_DIAG & 2)) store_entry(table, h, x, own, epoch, a1, a2, a3, pol); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
                 else table16[h] = (uint16_t)x;
             }
             __syncwarp();
         }
+#if TSQB_ENC_FIXED_GRID
+        // the next probe is position base + c (c >= 32) on every path out of the loop; windows stay on the grid 1 + 32k,
+        // a window that a long match (extension format) jumps over is skipped
+        base += c & ~31u;
+        c0 = c & 31u;
+#else
         base = chain_pending ? i : i + 1u;
+#endif
     }
 
     return e.finish(flags);
