@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     # dram__bytes_read.sum + dram__bytes_write.sum per launch of the 1 GB workload, from the committed ncu --set full
     # capture profiles/r01_v6_ncu_full_summary.txt (a profiler figure cannot be measured inside a timed run)
-    ap.add_argument("--traffic-encode", type=float, default=95.81e9, help="dram bytes per launch from an ncu --set full capture")
+    ap.add_argument("--traffic-encode", type=float, default=55.30e9, help="dram bytes per launch from an ncu --set full capture")
     ap.add_argument("--traffic-decode", type=float, default=5.86e9)
     args = ap.parse_args()
     if args.impl == "reference":

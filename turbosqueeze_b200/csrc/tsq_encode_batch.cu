@@ -60,6 +60,10 @@ constexpr int      kWarps = TSQB_ENC_WARPS;          // warps (= blocks in fligh
 #ifndef TSQB_ENC_DIAG
 #define TSQB_ENC_DIAG 0            // timing diagnostics, WRONG OUTPUT: 1 = table reads folded onto 256 sectors per block (L2-resident),
 #endif                             // 2 = commits not stored, 3 = both
+#ifndef TSQB_ENC_L2_64B
+#define TSQB_ENC_L2_64B 2          // table loads: 0 = plain, 1 = L2 fills 64 bytes per miss instead of a 128-byte line, 2 = that and no L1 allocation
+                                   // (27.86 / 27.60 / 27.36 ms; halves the DRAM bytes per probe)
+#endif
 #ifndef TSQB_ENC_ALIAS8
 #define TSQB_ENC_ALIAS8 0          // 1: alias tags taken from the word's top byte only (one byte load instead of two)
 #endif
@@ -138,8 +142,16 @@ __device__ __forceinline__ void load_entry(const uint4* table, uint32_t h, uint4
         asm volatile("ld.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                      : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h), "l"(pol) : "memory");
     else
+#if TSQB_ENC_L2_64B == 1
+        asm volatile("ld.global.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h) : "memory");
+#elif TSQB_ENC_L2_64B == 2
+        asm volatile("ld.global.L1::no_allocate.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h) : "memory");
+#else
         asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                      : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h) : "memory");
+#endif
 }
 
 // tag (word >> 17) of the 4-byte word at in[pos]: bits 17..31 live in bytes 2 and 3
