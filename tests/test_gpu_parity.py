@@ -132,11 +132,40 @@ def make_input(kind, n, seed):
     return W.fill(kind, n, seed=seed)
 
 
-@pytest.mark.parametrize("lanes", [34, 33, 32, 16, 8, 4, 2, 1])
+def test_decode_mixed_blocks_switch_copier_mode(torch, ctx, oracle):
+    """The default decoder picks its copier per block (lane per pair, or lane per symbol for incompressible blocks).
+    8192 blocks of 4 KiB (more than one round per block slot), text and random blocks interleaved irregularly, so
+    that every slot switches mode back and forth; every byte must come back."""
+    block, nb = 4096, 8192
+    n = block * nb - 1234
+    text = make_input("text", n, seed=77)
+    rnd = make_input("random", n, seed=78)
+    buf = text.copy()
+    pick = (np.arange(nb, dtype=np.uint64) * np.uint64(2654435761) >> np.uint64(7)) & np.uint64(3)
+    for b in np.nonzero(pick == 0)[0]:
+        lo, hi = int(b) * block, min((int(b) + 1) * block, n)
+        buf[lo:hi] = rnd[lo:hi]
+    slots, sizes, _ = oracle.encode_blocks(buf, n, block, 0)
+    assert (sizes > block).any() and (sizes < block * 0.9).any()
+    d_slots = torch.from_numpy(slots).cuda()
+    d_sizes = torch.from_numpy(sizes.astype(np.int32)).cuda()
+    for lanes in (0, 35, 34):
+        ctx.set_option("decode_lanes", lanes)
+        try:
+            out, osz = ctx.decode_blocks(d_slots, nb, block, 0, comp_sizes=d_sizes)
+            torch.cuda.synchronize()
+        finally:
+            ctx.set_option("decode_lanes", 0)
+        assert int(osz.cpu().numpy().sum()) == n
+        assert np.array_equal(out.cpu().numpy()[:n], buf[:n]), lanes
+
+
+@pytest.mark.parametrize("lanes", [35, 34, 33, 32, 16, 8, 4, 2, 1])
 @pytest.mark.parametrize("ext", [0, 1])
 def test_decode_restores_input(torch, ctx, oracle, lanes, ext):
-    """lanes 34 = walker + copier kernel (tsq_decode_split.cu, the default), 33 = warp-per-block step
-    kernel (tsq_decode_warp.cu), 1..32 = sub-warp pair-step kernel."""
+    """lanes 34 = walker + copier kernel (tsq_decode_split.cu, lane per symbol), 35 = the same with the lane-per-pair
+    copier (64 symbols per step; the extension format runs as 34), 33 = warp-per-block step kernel
+    (tsq_decode_warp.cu), 1..32 = sub-warp pair-step kernel."""
     if lanes == 33 and ext:
         pytest.skip("the v1 step kernel is no-extension only")
     ctx.set_option("decode_lanes", lanes)

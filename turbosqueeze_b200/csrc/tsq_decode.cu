@@ -140,15 +140,18 @@ static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream
 }
 
 cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
-cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st);
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair);
 
-// lanes: 0 = auto; 34 = walker + copier kernel (tsq_decode_split.cu, the default, both formats);
+// lanes: 0 = auto (35 for the no-extension format, 34 for the extension format);
+// 34 = walker + copier kernel (tsq_decode_split.cu), lane per symbol, both formats;
+// 35 = the same kernel choosing per block between the lane-per-pair copier (64 symbols per step) and, for (nearly)
+//      incompressible blocks, the lane-per-symbol one; no-extension format (the extension format runs as 34);
 // 1..32 = sub-warp kernel with that many lanes per block; 33 = force the warp-per-block
 // step kernel (tsq_decode_warp.cu), 32 = force the pair-step kernel at full warp width
 cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st)
 {
-    if (lanes <= 0) lanes = 34;
-    if (lanes == 34) return launch_decode_split(a, ext, sm_count, st);
+    if (lanes <= 0) lanes = ext ? 34 : 35;
+    if (lanes == 34 || lanes == 35) return launch_decode_split(a, ext, sm_count, st, lanes == 35);
     if (lanes == 33) return ext ? cudaErrorInvalidValue : launch_decode_warp(a, sm_count, st);
 #define TSQB_CASE(Wv) case Wv: return ext ? launch_decode_t<Wv, true>(a, sm_count, st) : launch_decode_t<Wv, false>(a, sm_count, st);
     switch (lanes) {

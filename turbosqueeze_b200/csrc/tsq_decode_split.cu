@@ -38,13 +38,22 @@ constexpr uint32_t kChunk    = 512;                  // bytes per bulk copy
 constexpr uint32_t kChunks   = 8;                    // ring slots
 constexpr uint32_t kInRing   = kChunk * kChunks;     // 4 KiB of stream per block slot
 constexpr uint32_t kInMask   = kInRing - 1;
-constexpr uint32_t kQueue    = 64;                   // descriptors per slot
+#ifndef TSQB_DEC_BULK4
+#define TSQB_DEC_BULK4 1           // development knob: walker takes 4 groups per limit test when far from every limit
+#endif
+#ifndef TSQB_DEC_QUEUE
+#define TSQB_DEC_QUEUE 128
+#endif
+constexpr uint32_t kQueue    = TSQB_DEC_QUEUE;       // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
 constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
 constexpr uint32_t kSteps    = kQueue / kPairs;      // steps the walker can be ahead
 constexpr uint32_t kLook     = 40;                   // stream bytes one pair can touch (1 + 1 + 16 + 16) + slack
 constexpr uint32_t kWalkers  = 2;                    // walker warps per CTA, slots dealt round-robin (1 or 2: 2.91 ms, 4: 3.05, 6: 3.12)
-constexpr uint32_t kMaxSlots = 32 - kWalkers;       // copier warps per CTA (copiers + walkers <= 1024 threads)
+#ifndef TSQB_DEC_LB
+#define TSQB_DEC_LB 1024                             // development knob: launch bound (threads per CTA); 896 lets ptxas use 72 registers
+#endif
+constexpr uint32_t kMaxSlots = TSQB_DEC_LB / 32 - kWalkers;   // copier warps per CTA (copiers + walkers <= TSQB_DEC_LB threads)
 
 
 template <uint32_t OUT_RING>
@@ -64,7 +73,8 @@ struct __align__(16) SlotSmem {
     uint32_t produced;       // walker -> copier: descriptors of this block published so far
     uint32_t ended;          // walker -> copier: the walk of this block is complete (set after the last `produced`)
     uint32_t end_j;          // output position the walk stopped at
-    uint32_t pad[3];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
+    uint32_t step_pairs;     // copier -> walker: descriptors per step for this block (16: lane per symbol, 32: lane per pair)
+    uint32_t pad[2];    // slot stride = 16 (mod 128): the walker's lanes do not pile onto 4 banks
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -158,6 +168,7 @@ __device__ __forceinline__ const uint8_t* stream_of(const DecodeArgs& a, uint64_
 template <uint32_t OUT_RING, bool EXT>
 __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t nslots, uint32_t widx, unsigned lane)
 {
+    uint32_t pmask = kPairs - 1u, smask = kQueue / kPairs - 1u;   // per block: descriptors per step - 1, step barriers in use - 1
     enum { P_DONE = 0, P_WAIT = 1, P_WALK = 2 };
     const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
     const uint32_t slot = lane * kWalkers + widx;             // walker warp widx owns slots widx, widx + kWalkers, ...
@@ -199,11 +210,38 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     continue;
                 }
                 const uint32_t have = (avail == nchunks) ? 0xffffffffu : avail * kChunk;
-                if ((k - cons) + 4u > kQueue) cons = ld_vol_u32(&sm.consumed);
+                if ((k - cons) + (TSQB_DEC_BULK4 ? 16u : 4u) > kQueue) cons = ld_vol_u32(&sm.consumed);
                 // ---- fast path: a whole group (control byte + 4 full pairs, tsq_decode.cpp:62-86) with no
                 // end-of-block inside it.  k % 4 == 0 here, so the 4 descriptors are contiguous in the queue.
                 const uint32_t p_safe = min(have, limit_al);
                 int groups = 0;
+#if TSQB_DEC_BULK4
+                // Four groups at once when even the longest possible ones (133 stream bytes, 128 output bytes each) stay clear of
+                // every limit: the per-group tests drop out of the serial chain.
+                if ((k & 3u) == 0 && p + 4u * 133u + 4u * kLook <= p_safe && (k - cons) + 16u <= kQueue && j + 4u * 128u + (EXT ? 512u : 128u) < size && !EXT) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        const uint32_t dsl = dbase + ((k & kQMask) << 3);
+                        const uint32_t c = ring_u8(p);
+                        uint32_t pp = p + 1u;
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const uint32_t nib = ring_u8(pp);
+                            put_desc(dsl + 8u * q, pp | ((c << (18 + 2 * q)) & 0x3000000u), j);
+                            const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+                            const uint32_t pay0 = (c & (0x80u >> (2 * q))) ? n0 + 2u : 3u;
+                            const uint32_t pay1 = (c & (0x40u >> (2 * q))) ? n1 + 1u : 2u;
+                            pp += pay0 + pay1;
+                            j += n0 + n1 + 2u;
+                        }
+                        p = pp;
+                        k += 4u;
+                        st_vol_u32(&sm.produced, k);
+                        if ((k & pmask) == 0) { mbar_arrive(&sm.full[steps & smask]); steps++; }
+                    }
+                    continue;
+                }
+#endif
 #pragma unroll 1
                 while (groups < 4 && (k & 3u) == 0 && p + 4u * kLook <= p_safe && (k - cons) + 4u <= kQueue && j + (EXT ? 512u : 128u) < size) {
                     const uint32_t dsl = dbase + ((k & kQMask) << 3);
@@ -223,7 +261,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     p = pp;
                     k += 4u;
                     st_vol_u32(&sm.produced, k);
-                    if ((k & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
+                    if ((k & pmask) == 0) { mbar_arrive(&sm.full[steps & smask]); steps++; }
                     groups++;
                 }
                 if (groups) continue;
@@ -245,11 +283,11 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     j = j1 + (two ? sym_len<EXT>(n1, (ctl & (0x40u >> (2u * q))) != 0) : 0u);
                     k++;
                     st_vol_u32(&sm.produced, k);
-                    if ((k & (kPairs - 1u)) == 0) { mbar_arrive(&sm.full[steps % kSteps]); steps++; }
+                    if ((k & pmask) == 0) { mbar_arrive(&sm.full[steps & smask]); steps++; }
                 } else {
                     st_vol_u32(&sm.end_j, j);
                     st_vol_u32(&sm.ended, 1u);
-                    mbar_arrive(&sm.full[steps % kSteps]); steps++;                 // closes the last (possibly empty) step
+                    mbar_arrive(&sm.full[steps & smask]); steps++;                  // closes the last (possibly empty) step
                     b += stride_slots;
                     phase = b < a.nb ? P_WAIT : P_DONE;
                 }
@@ -260,6 +298,8 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     limit_al = ld_vol_u32(&sm.limit_al);
                     nchunks  = ld_vol_u32(&sm.nchunks);
                     p        = ld_vol_u32(&sm.shift);
+                    pmask    = ld_vol_u32(&sm.step_pairs) - 1u;
+                    smask    = kQueue / (pmask + 1u) - 1u;
                     avail = 0; ctl = 0; j = 0; k = 0; cons = 0; size = 0xffffffffu;
                     phase = P_WALK;
                 }
@@ -311,21 +351,28 @@ __device__ __forceinline__ void store16(uint32_t base, uint32_t mask, uint32_t q
     }
 }
 
-template <uint32_t OUT_RING, bool EXT>
-__device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slot, uint32_t nslots, unsigned lane)
-{
-    constexpr uint32_t kOMask = OUT_RING - 1;
-    const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
+// Barrier bookkeeping of one block slot, carried from block to block (and between the two copiers)
+struct CopierState {
     uint32_t phase = 0;                    // bit s: parity the next completion of stream ring slot s will have
     uint32_t fphase = 0;                   // same for the step barriers
     uint32_t sc = 0;                       // running step counter (mirrors the walker's `steps`)
+};
+
+// Decodes blocks b0, b0 + stride_slots, ... (ONE: only b0) of slot `sm`.
+template <uint32_t OUT_RING, bool EXT, bool ONE>
+__device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0, uint64_t stride_slots, unsigned lane, CopierState& cs)
+{
+    constexpr uint32_t kOMask = OUT_RING - 1;
+    uint32_t& phase = cs.phase;
+    uint32_t& fphase = cs.fphase;
+    uint32_t& sc = cs.sc;
     uint8_t* oring = sm.out_ring;
     const uint8_t* iring = sm.in_ring;
     const uint32_t ibase = smem_u32(sm.in_ring), obase = smem_u32(sm.out_ring);
     const uint32_t bar_base = smem_u32(sm.bar), full_base = smem_u32(sm.full);
     const uint32_t pi = lane >> 1, half = lane & 1u;
 
-    for (uint64_t b = (uint64_t)blockIdx.x * nslots + slot; b < a.nb; b += stride_slots) {
+    for (uint64_t b = b0; b < a.nb; b += stride_slots) {
         uint32_t limit;
         const uint8_t* src = stream_of(a, b, limit);
         const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
@@ -364,6 +411,7 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
             st_vol_u32(&sm.limit_al, limit_al);
             st_vol_u32(&sm.nchunks, nchunks);
             st_vol_u32(&sm.shift, shift);
+            st_vol_u32(&sm.step_pairs, kPairs);
         }
         issue_upto(kChunks);
         __syncwarp();
@@ -527,11 +575,232 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint32_t slo
         }
         wait_upto(issued);                                                       // drain before the ring is reused
         __syncwarp();
+        if (ONE) break;
     }
 }
 
-template <uint32_t OUT_RING, bool EXT>
-__global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uint32_t nslots)
+// ------------------------------------------------------------------------------------------ copier, lane per PAIR
+// Same protocol as copier(), but a step is 32 descriptors = 64 symbols and lane L owns BOTH symbols of pair L (no-extension
+// format only: a step then produces at most 1 KiB, half of the smallest output ring).  Per symbol the work is the same;
+// what is paid once per step instead of twice -- barrier wait, descriptor and size-byte loads, the J0 / J1 reductions, chunk
+// bookkeeping, flush -- is about a third of copier()'s instructions, and the far-match loads of 64 symbols are in flight
+// together, so a block meets half as many DRAM-latency stalls.
+template <uint32_t OUT_RING>
+__device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b, unsigned lane, CopierState& cs)
+{
+    constexpr uint32_t kOMask = OUT_RING - 1;
+    constexpr uint32_t kPairs2 = 32, kSteps2 = kQueue / kPairs2;
+    static_assert(OUT_RING >= 2048, "a 64-symbol step writes up to 1 KiB");
+    uint32_t& phase = cs.phase;
+    uint32_t& fphase = cs.fphase;
+    uint32_t& sc = cs.sc;
+    uint8_t* oring = sm.out_ring;
+    const uint8_t* iring = sm.in_ring;
+    const uint32_t ibase = smem_u32(sm.in_ring), obase = smem_u32(sm.out_ring);
+    const uint32_t bar_base = smem_u32(sm.bar), full_base = smem_u32(sm.full);
+
+    {
+        uint32_t limit;
+        const uint8_t* src = stream_of(a, b, limit);
+        const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+        const uint8_t* src_al = src - shift;
+        const uint32_t limit_al = shift + limit;
+        const uint32_t total_al = (limit_al + 15u) & ~15u;
+        const uint32_t nchunks = (total_al + kChunk - 1) / kChunk;
+        uint32_t issued = 0, waited = 0, cur_chunk = 0;
+
+        auto issue_upto = [&](uint32_t want) {
+            want = min(want, nchunks);
+            if (lane == 0)
+                for (uint32_t n = issued; n < want; n++) {
+                    const uint32_t at = n * kChunk, bytes = min(kChunk, total_al - at);
+                    mbar_expect_tx(&sm.bar[n % kChunks], bytes);
+                    bulk_load(sm.in_ring + (at & kInMask), src_al + at, bytes, &sm.bar[n % kChunks]);
+                }
+            issued = max(issued, want);
+        };
+        auto wait_upto = [&](uint32_t want) {
+            want = min(want, issued);
+            for (; waited < want; waited++) {
+                const uint32_t s = waited % kChunks;
+                mbar_wait_addr(bar_base + 8u * s, (phase >> s) & 1u);
+                phase ^= 1u << s;
+            }
+        };
+
+        uint32_t kc = 0;
+        if (lane == 0) {
+            st_vol_u32(&sm.produced, 0u);
+            st_vol_u32(&sm.consumed, 0u);
+            st_vol_u32(&sm.ended, 0u);
+            st_vol_u32(&sm.phase_bits, phase);
+            st_vol_u32(&sm.limit_al, limit_al);
+            st_vol_u32(&sm.nchunks, nchunks);
+            st_vol_u32(&sm.shift, shift);
+            st_vol_u32(&sm.step_pairs, kPairs2);
+        }
+        issue_upto(kChunks);
+        __syncwarp();
+        if (lane == 0) { __threadfence_block(); st_vol_u32(&sm.ready, (uint32_t)b + 1u); }
+        wait_upto(1);
+
+        auto rb = [&](uint32_t k) -> uint32_t { return iring[k & kInMask]; };
+        uint32_t size = rb(shift) | (rb(shift + 1u) << 8) | (rb(shift + 2u) << 16);   // tsq_decode.cpp:49-51
+        const bool ok = size <= kBlockMax && size <= a.ostride && nchunks != 0;
+        if (!ok) size = 0;
+        if (lane == 0) a.osizes[b] = size;
+
+        uint8_t* o = a.out + b * a.ostride;
+        const uint32_t oal = (uint32_t)(reinterpret_cast<uintptr_t>(o) & 15u);
+        uint8_t* o_al = o - oal;
+        uint32_t F = oal;
+
+        auto flush_units = [&](uint32_t E) {
+            for (uint32_t at = F + 16u * lane; at < E; at += 512u) {
+                uint4 x;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
+                *reinterpret_cast<uint4*>(o_al + at) = x;
+            }
+            F = E;
+        };
+        auto flush = [&](uint32_t E, bool final) {
+            if (!final) E &= ~15u;
+            if (F >= E) return;
+            if (F & 15u) {
+                const uint32_t h = min(E, (F + 15u) & ~15u);
+                if (lane < h - F) o_al[F + lane] = oring[(F + lane) & kOMask];
+                F = h;
+            }
+            flush_units(E & ~15u);
+            if (F < E) {
+                if (lane < E - F) o_al[F + lane] = oring[(F + lane) & kOMask];
+                F = E;
+            }
+        };
+        // raw words of a far source (bytes an earlier step flushed to HBM); never touches a word past the source
+        auto far_load = [&](uint32_t srcq, uint32_t len, uint32_t w[5]) {
+            const uintptr_t ad = reinterpret_cast<uintptr_t>(o_al + srcq);
+            const uint32_t* g32 = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+#pragma unroll
+            for (int m = 0; m < 5; m++) w[m] = ((uint32_t)(ad & 3u) + len > 4u * m) ? __ldcg(g32 + m) : 0u;
+        };
+        // one pending symbol (source inside this step's output), lane-per-byte, after everything before it is in place
+        auto copy_in_order = [&](uint32_t s_q, uint32_t s_src, uint32_t s_len) {
+            __syncwarp();
+            if (lane < s_len) {
+                uint32_t byte;
+                asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((s_src + lane) & kOMask)) : "memory");
+                asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((s_q + lane) & kOMask)), "r"(byte) : "memory");
+            }
+        };
+
+        bool done = false;
+        while (!done) {
+            {
+                const uint32_t s = sc % kSteps2;
+                mbar_wait_addr(full_base + 8u * s, (fphase >> s) & 1u);
+                fphase ^= 1u << s;
+                sc++;
+            }
+            const uint32_t np = min(ld_vol_u32(&sm.produced) - kc, kPairs2);
+            done = np < kPairs2;
+            const uint2 d = ld_vol_u64(&sm.desc[(kc + lane) & kQMask]);
+            if (np) {
+                const uint32_t plast = __shfl_sync(FULL, d.x & 0xFFFFFFu, np - 1u);
+                if ((plast + kLook - 2u) / kChunk >= waited) wait_upto((plast + kLook - 2u) / kChunk + 1u);
+
+                // ---- lane L: both symbols of pair L (tsq_decode.cpp:68-86)
+                const bool active = lane < np;
+                const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y;
+                const uint32_t nib = rb(pp);
+                const bool l0 = (d.x & (0x80u << 18)) != 0, l1 = (d.x & (0x40u << 18)) != 0;
+                uint32_t len0 = (nib >> 4) + 1u, len1 = (nib & 15u) + 1u;
+                const uint32_t sp0 = pp + 1u, sp1 = sp0 + (l0 ? len0 : 2u);
+                const uint32_t dst0 = jp, dst1 = jp + len0;
+                bool act0 = active && dst0 < size, act1 = active && dst1 < size;
+                len0 = act0 ? min(len0, size - dst0) : 0u;
+                len1 = act1 ? min(len1, size - dst1) : 0u;
+                const uint32_t q0 = dst0 + oal, q1 = dst1 + oal;
+                uint32_t src0 = 0, src1 = 0;
+                if (act0 && !l0) {
+                    const uint32_t off = rb(sp0) | (rb(sp0 + 1u) << 8);          // :69,73
+                    act0 = off <= jp;                                            // corrupt stream guard
+                    src0 = jp - off + oal;
+                }
+                if (act1 && !l1) {
+                    const uint32_t off = rb(sp1) | (rb(sp1 + 1u) << 8);          // :82: the same pair start
+                    act1 = off <= jp;
+                    src1 = jp - off + oal;
+                }
+                const uint32_t J0 = __shfl_sync(FULL, q0, 0);
+                const uint32_t J1 = __reduce_max_sync(FULL, max(act0 ? q0 + len0 : 0u, act1 ? q1 + len1 : 0u));
+
+                // ---- round 0: literals and matches whose source precedes this step's output
+                const bool now0 = act0 && (l0 || src0 + len0 <= J0), now1 = act1 && (l1 || src1 + len1 <= J0);
+                const bool pend0 = act0 && !now0, pend1 = act1 && !now1;
+                const bool far0 = now0 && !l0 && src0 + OUT_RING < J1 + 16u, far1 = now1 && !l1 && src1 + OUT_RING < J1 + 16u;
+                uint32_t w0[5], w1[5];
+                if (far0) far_load(src0, len0, w0);                              // both symbols' far loads fly together
+                if (far1) far_load(src1, len1, w1);
+                uint32_t v0[4] = {0, 0, 0, 0}, v1[4] = {0, 0, 0, 0};
+                {
+                    const uint32_t fbase = l0 ? ibase : obase, fmask = l0 ? kInMask : kOMask, fpos = l0 ? sp0 : src0;
+                    const bool sm_src = now0 && !far0;
+                    const bool wrap = __any_sync(FULL, sm_src && ((fpos & fmask) + 20u > fmask + 1u));
+                    if (sm_src) load16_smem(fbase, fmask, fpos, v0, wrap);
+                }
+                {
+                    const uint32_t fbase = l1 ? ibase : obase, fmask = l1 ? kInMask : kOMask, fpos = l1 ? sp1 : src1;
+                    const bool sm_src = now1 && !far1;
+                    const bool wrap = __any_sync(FULL, sm_src && ((fpos & fmask) + 20u > fmask + 1u));
+                    if (sm_src) load16_smem(fbase, fmask, fpos, v1, wrap);
+                }
+                if (far0) {
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(o_al + src0) & 3u) * 8u;
+#pragma unroll
+                    for (int m = 0; m < 4; m++) v0[m] = __funnelshift_r(w0[m], w0[m + 1], sh);
+                }
+                if (far1) {
+                    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(o_al + src1) & 3u) * 8u;
+#pragma unroll
+                    for (int m = 0; m < 4; m++) v1[m] = __funnelshift_r(w1[m], w1[m + 1], sh);
+                }
+                if (now0) store16(obase, kOMask, q0, v0, (q0 & kOMask) + 16u > OUT_RING, (1u << len0) - 1u);
+                if (now1) store16(obase, kOMask, q1, v1, (q1 & kOMask) + 16u > OUT_RING, (1u << len1) - 1u);
+
+                // ---- symbols whose source lies inside this step's output: in position order (pair by pair, first
+                // symbol before second); sources always precede their own pair (tsq_encode.cpp:139-141)
+                uint32_t pm0 = __ballot_sync(FULL, pend0), pm1 = __ballot_sync(FULL, pend1);
+                while (pm0 | pm1) {
+                    const uint32_t pl = (uint32_t)__ffs((int)(pm0 | pm1)) - 1u;
+                    const bool first = (pm0 >> pl) & 1u;                         // warp-uniform: this pair's first symbol is still due
+                    const uint32_t s_q = __shfl_sync(FULL, first ? q0 : q1, pl), s_src = __shfl_sync(FULL, first ? src0 : src1, pl),
+                                   s_len = __shfl_sync(FULL, first ? len0 : len1, pl);
+                    copy_in_order(s_q, s_src, s_len);
+                    if (first) pm0 &= ~(1u << pl); else pm1 &= ~(1u << pl);
+                }
+                __syncwarp();
+                if (F & 15u) flush(J1, false); else if ((J1 & ~15u) > F) flush_units(J1 & ~15u);
+                kc += np;
+                // recycle the stream ring behind this step: every pair up to the last one is consumed, so the chunks before
+                // the one the last pair's size byte sits in are free (a step reads up to 1 KiB of stream; freeing only
+                // up to the step's FIRST pair would leave the walker less than one step of look-ahead on literal data)
+                const uint32_t c0 = plast / kChunk;
+                if (c0 != cur_chunk) { cur_chunk = c0; issue_upto(c0 + kChunks); }
+            }
+            if (done) {
+                __syncwarp();
+                flush(min(ld_vol_u32(&sm.end_j), size) + oal, true);
+            }
+            if (lane == 0) st_vol_u32(&sm.consumed, kc);
+        }
+        wait_upto(issued);
+        __syncwarp();
+    }
+}
+
+template <uint32_t OUT_RING, bool EXT, uint32_t PAIRS, int LB>
+__global__ void __launch_bounds__(LB, 1) decode_split_kernel(DecodeArgs a, uint32_t nslots)
 {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     SlotSmem<OUT_RING>* slots = reinterpret_cast<SlotSmem<OUT_RING>*>(smem_raw);
@@ -549,30 +818,45 @@ __global__ void __launch_bounds__(1024, 1) decode_split_kernel(DecodeArgs a, uin
         }
     }
     __syncthreads();
-    if (wid < nslots) copier<OUT_RING, EXT>(a, slots[wid], wid, nslots, lane);
-    else              walker<OUT_RING, EXT>(a, slots, nslots, wid - nslots, lane);
+    if (wid < nslots) {
+        const uint64_t stride_slots = (uint64_t)gridDim.x * nslots, b0 = (uint64_t)blockIdx.x * nslots + wid;
+        CopierState cs;
+        if constexpr (PAIRS == 32) {
+            // Per block: lane per pair (64 symbols per step) unless the block is (nearly) incompressible.  A stream of
+            // 16-byte literals is walker-bound, and there the 32-descriptor hand-over costs more than it saves (measured:
+            // uniform random data 942 vs 669 GB/s, text 341 vs 371 GB/s).
+            for (uint64_t b = b0; b < a.nb; b += stride_slots) {
+                uint32_t limit;
+                stream_of(a, b, limit);
+                const bool dense = (uint64_t)limit * 16u >= a.ostride * 15u;      // C/U >= 0.94, or sizes not given
+                if (dense) copier<OUT_RING, EXT, true>(a, slots[wid], b, stride_slots, lane, cs);
+                else       copier_pairs<OUT_RING>(a, slots[wid], b, lane, cs);
+            }
+        } else copier<OUT_RING, EXT, false>(a, slots[wid], b0, stride_slots, lane, cs);
+    } else walker<OUT_RING, EXT>(a, slots, nslots, wid - nslots, lane);
 }
 
-template <uint32_t OUT_RING, bool EXT>
+template <uint32_t OUT_RING, bool EXT, uint32_t PAIRS = kPairs, int LB = TSQB_DEC_LB>
 cudaError_t launch_split_t(const DecodeArgs& a, uint32_t nslots, unsigned ctas, cudaStream_t st)
 {
     const size_t smem = sizeof(SlotSmem<OUT_RING>) * nslots;
-    cudaError_t e = cudaFuncSetAttribute(decode_split_kernel<OUT_RING, EXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(decode_split_kernel<OUT_RING, EXT, PAIRS, LB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    decode_split_kernel<OUT_RING, EXT><<<ctas, (nslots + kWalkers) * 32, smem, st>>>(a, nslots);
+    decode_split_kernel<OUT_RING, EXT, PAIRS, LB><<<ctas, (nslots + kWalkers) * 32, smem, st>>>(a, nslots);
     return cudaGetLastError();
 }
 
 }  // namespace
 
 // One CTA per SM; every CTA owns `nslots` block slots (copier warps) and kWalkers walker warps.
-cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st)
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair)
 {
     if (a.nb == 0) return cudaSuccess;
     const size_t budget = 227u * 1024u;
     uint64_t per_sm = (a.nb + sm_count - 1) / sm_count;
     uint32_t nslots = (uint32_t)(per_sm < kMaxSlots ? per_sm : kMaxSlots);
     if (nslots == 0) nslots = 1;
+    lane_per_pair = lane_per_pair && !ext;
     // a step of the extension format can produce 32 x 64 bytes: the output ring must be >= 4 KiB
     if (ext) while (sizeof(SlotSmem<4096>) * nslots > budget) nslots--;
     unsigned ctas = (unsigned)((a.nb + nslots - 1) / nslots);
@@ -586,6 +870,14 @@ cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cud
     // Measured (profiles/r01_experiments.md): a ring that fills all 227 KB leaves the SM without L1 and is ~20 % slower
     // than a 2 KiB ring (3.73 vs 3.03 ms on the bench workload); 1 KiB is no faster.  Keep >= 43 KB for L1.
     const size_t roomy = 184u * 1024u;
+    // lane-per-pair copier (64 symbols per step, no-extension format): 896-thread launch bound = 72 registers
+    if (lane_per_pair) {
+        if ((nslots + kWalkers) * 32u > 896u) return launch_split_t<2048, false, 32, 1024>(a, nslots, ctas, st);   // 27..30 slots: 64 registers
+        if (sizeof(SlotSmem<16384>) * nslots <= roomy) return launch_split_t<16384, false, 32, 896>(a, nslots, ctas, st);
+        if (sizeof(SlotSmem<8192>) * nslots <= roomy)  return launch_split_t<8192, false, 32, 896>(a, nslots, ctas, st);
+        if (sizeof(SlotSmem<4096>) * nslots <= roomy)  return launch_split_t<4096, false, 32, 896>(a, nslots, ctas, st);
+        return launch_split_t<2048, false, 32, 896>(a, nslots, ctas, st);
+    }
     if (sizeof(SlotSmem<16384>) * nslots <= roomy) return launch_split_t<16384, false>(a, nslots, ctas, st);
     if (sizeof(SlotSmem<8192>) * nslots <= roomy)  return launch_split_t<8192, false>(a, nslots, ctas, st);
     if (sizeof(SlotSmem<4096>) * nslots <= roomy)  return launch_split_t<4096, false>(a, nslots, ctas, st);
