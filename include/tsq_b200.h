@@ -77,8 +77,9 @@ uint64_t tsqb_slot_stride(uint32_t block_size);
  *                   3 = warp-per-block token batches (tsq_encode_batch.cu)
  *   "encode_slots"  0 = auto: hash tables (= blocks) in flight
  *   "encode_fat"    table format of the batch encoder: -1 = auto, 0 = 2^17 x u16, 1 = 32-byte sector entries
- *   "decode_lanes"  0 = auto (34), 34 = walker + copier kernel (tsq_decode_split.cu), 33 = v1 warp kernel (no-ext only),
- *                   1,2,4,8,16,32 = sub-warp pair-step kernel with that many lanes per block
+ *   "decode_lanes"  0 = auto (35, or 34 for the extension format); 35 = walker + copier kernel (tsq_decode_split.cu) choosing
+ *                   per block between the lane-per-pair and the lane-per-symbol copier, 34 = lane per symbol only,
+ *                   33 = v1 warp kernel (no-ext only), 1,2,4,8,16,32 = sub-warp pair-step kernel with that many lanes per block
  *   "pipeline"      1 = the host-buffer calls overlap PCIe copies with kernels in chunks, 0 = one-shot staging
  *   "pipeline_min"  bytes below which the host-buffer calls stage in one shot */
 int tsqb_set_option(tsqb_context* ctx, const char* key, int64_t value);
