@@ -77,6 +77,7 @@ struct tsqb_context {
     int sm_count = 148;
     int encode_impl = 0;       // 0 auto, 1 scalar, 2 warp
     int decode_lanes = 0;      // 0 auto
+    int decode_slots = 0;      // 0 auto; else at most this many block slots (copier warps) per CTA of the walker + copier kernel
     int64_t encode_slots = 0;  // 0 auto
     int encode_hints = 0;      // see EncodeArgs::hints
     int encode_fat = -1;       // batch encoder table format: -1 auto, 0 u16 tables, 1 sector entries
@@ -160,6 +161,7 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
     if (!c || !key) return 1;
     if (!strcmp(key, "encode_impl"))  { c->encode_impl = (int)v; return 0; }
     if (!strcmp(key, "decode_lanes")) { c->decode_lanes = (int)v; return 0; }
+    if (!strcmp(key, "decode_slots")) { if (v < 0 || v > 30) return 1; c->decode_slots = (int)v; return 0; }
     if (!strcmp(key, "encode_slots")) { c->encode_slots = v; return 0; }
     if (!strcmp(key, "encode_fat")) { c->encode_fat = (int)v; return 0; }
     if (!strcmp(key, "encode_hints")) { c->encode_hints = (int)v; return 0; }
@@ -223,7 +225,7 @@ extern "C" int tsqb_decode_blocks(tsqb_context* c, const uint8_t* d_comp, const 
     DecodeArgs a;
     a.comp = d_comp; a.offs = d_offsets; a.stride = stride; a.csizes = d_comp_sizes; a.nb = nb;
     a.out = d_out; a.ostride = out_stride; a.osizes = d_out_sizes;
-    CU(launch_decode(a, c->decode_lanes, with_ext != 0, c->sm_count, (cudaStream_t)stream));
+    CU(launch_decode(a, c->decode_lanes, with_ext != 0, c->sm_count, (cudaStream_t)stream, c->decode_slots));
     g_launches += 1;
     return 0;
 }

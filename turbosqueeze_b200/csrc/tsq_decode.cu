@@ -140,7 +140,7 @@ static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream
 }
 
 cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
-cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair);
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair, int slot_cap);
 
 // lanes: 0 = auto (35 for the no-extension format, 34 for the extension format);
 // 34 = walker + copier kernel (tsq_decode_split.cu), lane per symbol, both formats;
@@ -148,10 +148,10 @@ cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cud
 //      incompressible blocks, the lane-per-symbol one; no-extension format (the extension format runs as 34);
 // 1..32 = sub-warp kernel with that many lanes per block; 33 = force the warp-per-block
 // step kernel (tsq_decode_warp.cu), 32 = force the pair-step kernel at full warp width
-cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st)
+cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st, int slot_cap)
 {
     if (lanes <= 0) lanes = ext ? 34 : 35;
-    if (lanes == 34 || lanes == 35) return launch_decode_split(a, ext, sm_count, st, lanes == 35);
+    if (lanes == 34 || lanes == 35) return launch_decode_split(a, ext, sm_count, st, lanes == 35, slot_cap);
     if (lanes == 33) return ext ? cudaErrorInvalidValue : launch_decode_warp(a, sm_count, st);
 #define TSQB_CASE(Wv) case Wv: return ext ? launch_decode_t<Wv, true>(a, sm_count, st) : launch_decode_t<Wv, false>(a, sm_count, st);
     switch (lanes) {

@@ -829,7 +829,10 @@ __global__ void __launch_bounds__(LB, 1) decode_split_kernel(DecodeArgs a, uint3
                 uint32_t limit;
                 stream_of(a, b, limit);
                 const bool dense = (uint64_t)limit * 16u >= a.ostride * 15u;      // C/U >= 0.94, or sizes not given
-                if (dense) copier<OUT_RING, EXT, true>(a, slots[wid], b, stride_slots, lane, cs);
+                // ... and unless it is almost all 16-byte matches (C/U < 0.3): periodic data, where every match copies from
+                // inside its own step and the in-order copies dominate (8-byte period: 6.5 vs 8.3 ms per 2 GiB)
+                const bool runs = (uint64_t)limit * 10u < a.ostride * 3u;
+                if (dense || runs) copier<OUT_RING, EXT, true>(a, slots[wid], b, stride_slots, lane, cs);
                 else       copier_pairs<OUT_RING>(a, slots[wid], b, lane, cs);
             }
         } else copier<OUT_RING, EXT, false>(a, slots[wid], b0, stride_slots, lane, cs);
@@ -849,16 +852,26 @@ cudaError_t launch_split_t(const DecodeArgs& a, uint32_t nslots, unsigned ctas, 
 }  // namespace
 
 // One CTA per SM; every CTA owns `nslots` block slots (copier warps) and kWalkers walker warps.
-cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair)
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair, int slot_cap)
 {
     if (a.nb == 0) return cudaSuccess;
     const size_t budget = 227u * 1024u;
-    uint64_t per_sm = (a.nb + sm_count - 1) / sm_count;
-    uint32_t nslots = (uint32_t)(per_sm < kMaxSlots ? per_sm : kMaxSlots);
-    if (nslots == 0) nslots = 1;
+    const uint64_t per_sm = (a.nb + sm_count - 1) / sm_count;
     lane_per_pair = lane_per_pair && !ext;
-    // a step of the extension format can produce 32 x 64 bytes: the output ring must be >= 4 KiB
-    if (ext) while (sizeof(SlotSmem<4096>) * nslots > budget) nslots--;
+    // How many block slots per CTA.  Measured (profiles/r01_experiments.md): with blocks of 64 KiB and more a round of
+    // blocks takes ~1.7x longer once the slots need more than the 196 KB shared-memory carve-out (the SM then keeps
+    // 28 KB of L1 instead of 60 KB), and within that limit fewer slots make a faster round.  So: stay inside the
+    // carve-out, take the fewest rounds that allows, and spread the blocks evenly over those rounds.  Small blocks
+    // (< 64 KiB) are set-up bound and want every slot the CTA can hold.
+    // (a step of the extension format can produce 32 x 64 bytes: its output ring must be >= 4 KiB)
+    const size_t slot_bytes = ext ? sizeof(SlotSmem<4096>) : sizeof(SlotSmem<2048>);
+    uint32_t cap = kMaxSlots;
+    while (slot_bytes * cap > budget) cap--;
+    if (a.ostride >= 65536u) while (cap > 1 && slot_bytes * cap > 195u * 1024u) cap--;
+    if (slot_cap > 0 && cap > (uint32_t)slot_cap) cap = (uint32_t)slot_cap;            // option "decode_slots"
+    const uint64_t rounds = (per_sm + cap - 1) / cap;
+    uint32_t nslots = (uint32_t)((per_sm + rounds - 1) / rounds);
+    if (nslots == 0) nslots = 1;
     unsigned ctas = (unsigned)((a.nb + nslots - 1) / nslots);
     if (ctas > (unsigned)sm_count) ctas = (unsigned)sm_count;
     // output ring as large as 227 KB of shared memory allows

@@ -49,7 +49,7 @@ bool        encode_wants_fat(int impl, uint32_t n_slots);
 uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);
 
 // lanes: lanes cooperating on one block (1..32, power of two)
-cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st);
+cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st, int slot_cap = 0);
 int         decode_lanes_auto(uint64_t nb, int sm_count);
 
 cudaError_t launch_pack(const uint8_t* slots, uint64_t stride, const uint32_t* sizes, uint64_t nb,
