@@ -49,7 +49,10 @@ constexpr uint32_t kQMask    = kQueue - 1;
 constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
 constexpr uint32_t kSteps    = kQueue / kPairs;      // steps the walker can be ahead
 constexpr uint32_t kLook     = 40;                   // stream bytes one pair can touch (1 + 1 + 16 + 16) + slack
-constexpr uint32_t kWalkers  = 2;                    // walker warps per CTA, slots dealt round-robin (1 or 2: 2.91 ms, 4: 3.05, 6: 3.12)
+#ifndef TSQB_DEC_WALKERS
+#define TSQB_DEC_WALKERS 2
+#endif
+constexpr uint32_t kWalkers  = TSQB_DEC_WALKERS;                    // walker warps per CTA, slots dealt round-robin (1 or 2: 2.91 ms, 4: 3.05, 6: 3.12)
 #ifndef TSQB_DEC_LB
 #define TSQB_DEC_LB 1024                             // development knob: launch bound (threads per CTA); 896 lets ptxas use 72 registers
 #endif
