@@ -60,6 +60,9 @@ constexpr int      kWarps = TSQB_ENC_WARPS;          // warps (= blocks in fligh
 #ifndef TSQB_ENC_DIAG
 #define TSQB_ENC_DIAG 0            // timing diagnostics, WRONG OUTPUT: 1 = table reads folded onto 256 sectors per block (L2-resident),
 #endif                             // 2 = commits not stored, 3 = both
+#ifndef TSQB_ENC_L2POL
+#define TSQB_ENC_L2POL 0           // development knob: bit 0 = table loads carry an L2 evict_first policy, bit 1 = commits an evict_last one
+#endif
 #ifndef TSQB_ENC_L2_64B
 #define TSQB_ENC_L2_64B 2          // table loads: 0 = plain, 1 = L2 fills 64 bytes per miss instead of a 128-byte line, 2 = that and no L1 allocation
                                    // (27.86 / 27.60 / 27.36 ms; halves the DRAM bytes per probe)
@@ -139,7 +142,7 @@ __device__ __forceinline__ void store_bytes(uint32_t ad, const uint32_t v[4], ui
 __device__ __forceinline__ void load_entry(const uint4* table, uint32_t h, uint4& A, uint4& B, uint64_t pol)
 {
     if (pol)
-        asm volatile("ld.global.L2::cache_hint.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
+        asm volatile("ld.global.L1::no_allocate.L2::cache_hint.L2::64B.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8], %9;"
                      : "=r"(A.x), "=r"(A.y), "=r"(A.z), "=r"(A.w), "=r"(B.x), "=r"(B.y), "=r"(B.z), "=r"(B.w) : "l"(table + 2u * h), "l"(pol) : "memory");
     else
 #if TSQB_ENC_L2_64B == 1
@@ -390,6 +393,9 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
     const uint32_t hints = TSQB_ENC_HINTS ? hints_ : 0u;
     uint64_t pol = 0;                                                  // experiment: table traffic marked evict-first in L2
     if (hints & 1u) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    uint64_t pol_ld = pol, pol_st = pol;
+    if (TSQB_ENC_L2POL & 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_ld));
+    if (TSQB_ENC_L2POL & 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_st));
     BlockEncoder e;
     e.stream_out = (hints & 2u) != 0;
     e.in = in; e.size = size; e.lane = lane;
@@ -428,7 +434,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         uint32_t tab_cand, m_tab;
         if constexpr (FAT) {
             uint4 A = make_uint4(0, 0, 0, 0), B = A;                   // all-zero = an entry of no epoch
-            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, (TSQB_ENC_DIAG & 1) ? (h & 255u) : h, A, B, pol);
+            if ((ws.written[h >> 7] >> ((h >> 2) & 31u)) & 1u) load_entry(table, (TSQB_ENC_DIAG & 1) ? (h & 255u) : h, A, B, pol_ld);
             // An entry of another epoch is the reference's zero entry: candidate = start of the 64 KiB segment
             // (expand_pos(0, x)), one shared, cache-resident location.
             const bool live = A.z == (uint32_t)epoch && B.z == (uint32_t)(epoch >> 32);
@@ -652,7 +658,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         {
             const uint32_t mine = M & inP;
             if (((inP >> lane) & 1u) && (mine >> lane) == 1u) {
-                if constexpr (FAT) { if (!(TSQB_ENC_DIAG & 2)) store_entry(table, h, x, own, epoch, a1, a2, a3, pol); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
+                if constexpr (FAT) { if (!(TSQB_ENC_DIAG & 2)) store_entry(table, h, x, own, epoch, a1, a2, a3, pol_st); atomicOr(&ws.written[h >> 7], 1u << ((h >> 2) & 31u)); }
                 else table16[h] = (uint16_t)x;
             }
             __syncwarp();
