@@ -79,7 +79,7 @@ struct tsqb_context {
     int decode_lanes = 0;      // 0 auto
     int decode_slots = 0;      // 0 auto; else at most this many block slots (copier warps) per CTA of the walker + copier kernel
     int64_t encode_slots = 0;  // 0 auto
-    int encode_hints = 0;      // see EncodeArgs::hints
+    int encode_hints = 0;      // see EncodeArgs::hints (a development option; a default build ignores it)
     int encode_fat = -1;       // batch encoder table format: -1 auto, 0 u16 tables, 1 sector entries
     DevBuf tables;             // hash tables of the blocks in flight (zeroed when allocated: epoch 0 = empty)
     DevBuf ftables;            // batch encoder: 32-byte entries, only ever written by that kernel, zeroed at allocation

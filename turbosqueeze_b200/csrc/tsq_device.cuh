@@ -24,7 +24,8 @@ struct EncodeArgs {
     uint64_t       epoch;     // batch encoder: entries written under another epoch are empty (no per-block zeroing)
     uint32_t       fat;       // batch encoder: 1 = sector entries (kFatTableBytes per table), 0 = u16 tables
     uint32_t       n_slots;
-    uint32_t       hints = 0; // batch encoder experiments: 1 = table traffic evict-first in L2, 2 = streaming output stores
+    uint32_t       hints = 0; // batch encoder experiments (only in a build with -DTSQB_ENC_HINTS=1; ignored otherwise):
+                              // 1 = table traffic evict-first in L2, 2 = streaming output stores, 4 / 8 = L2 prefetches
 };
 
 struct DecodeArgs {
