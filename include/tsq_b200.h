@@ -80,6 +80,7 @@ uint64_t tsqb_slot_stride(uint32_t block_size);
  *   "decode_lanes"  0 = auto (35, or 34 for the extension format); 35 = walker + copier kernel (tsq_decode_split.cu) choosing
  *                   per block between the lane-per-pair and the lane-per-symbol copier, 34 = lane per symbol only,
  *                   33 = v1 warp kernel (no-ext only), 1,2,4,8,16,32 = sub-warp pair-step kernel with that many lanes per block
+ *   "decode_slots"  0 = auto; 1..30 = at most this many block slots (copier warps) per CTA of the walker + copier kernel
  *   "pipeline"      1 = the host-buffer calls overlap PCIe copies with kernels in chunks, 0 = one-shot staging
  *   "pipeline_min"  bytes below which the host-buffer calls stage in one shot */
 int tsqb_set_option(tsqb_context* ctx, const char* key, int64_t value);

@@ -90,7 +90,7 @@ struct tsqb_context {
     // pipelined host path: copy-in / copy-out streams, one compute stream + events per chunk in flight
     static constexpr int kPipe = 16;           // most chunks a buffer is cut into
     int pipe_taper = 0;                        // compress: chunks shrink towards the end (option "pipe_taper")
-    int pipe_chunks = 4;                       // chunks actually used (option "pipe_chunks", 1..kPipe)
+    int pipe_chunks = 6;                       // chunks actually used (option "pipe_chunks", 1..kPipe; 4 / 6 / 8 / 12: 70.3 / 68.9 / 70.6 / 80.7 ms per GB round trip)
     cudaStream_t s_in = nullptr, s_out = nullptr, s_chunk[kPipe] = {};
     cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
     uint64_t* h_len = nullptr;                 // pinned: per-chunk container length
