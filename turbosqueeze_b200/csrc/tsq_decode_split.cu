@@ -220,28 +220,34 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                 int groups = 0;
 #if TSQB_DEC_BULK4
                 // Four groups at once when even the longest possible ones (133 stream bytes, 128 output bytes each) stay clear of
-                // every limit: the per-group tests drop out of the serial chain.
-                if ((k & 3u) == 0 && p + 4u * 133u + 4u * kLook <= p_safe && (k - cons) + 16u <= kQueue && j + 4u * 128u + (EXT ? 512u : 128u) < size && !EXT) {
+                // every limit -- and of the end of the stream ring, so that the walk can use a plain shared-memory pointer: the
+                // per-group tests and the ring wrap (mask + base) drop out of the serial chain (load, 3 ALU, load).
+                if ((k & 3u) == 0 && p + 4u * 133u + 4u * kLook <= p_safe && (k - cons) + 16u <= kQueue && j + 4u * 128u + (EXT ? 512u : 128u) < size && !EXT &&
+                    (p & kInMask) + 4u * 133u + 8u <= kInRing) {
+                    uint32_t pr = rbase + (p & kInMask);          // shared address of stream position p
+                    const uint32_t dlt = p - pr;                  // stream position = shared address + dlt
+                    auto lds_u8 = [](uint32_t ad) -> uint32_t { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ad)); return v; };
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         const uint32_t dsl = dbase + ((k & kQMask) << 3);
-                        const uint32_t c = ring_u8(p);
-                        uint32_t pp = p + 1u;
+                        const uint32_t c = lds_u8(pr);
+                        uint32_t prp = pr + 1u;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
-                            const uint32_t nib = ring_u8(pp);
-                            put_desc(dsl + 8u * q, pp | ((c << (18 + 2 * q)) & 0x3000000u), j);
+                            const uint32_t nib = lds_u8(prp);
+                            put_desc(dsl + 8u * q, (prp + dlt) | ((c << (18 + 2 * q)) & 0x3000000u), j);
                             const uint32_t n0 = nib >> 4, n1 = nib & 15u;
                             const uint32_t pay0 = (c & (0x80u >> (2 * q))) ? n0 + 2u : 3u;
                             const uint32_t pay1 = (c & (0x40u >> (2 * q))) ? n1 + 1u : 2u;
-                            pp += pay0 + pay1;
+                            prp += pay0 + pay1;
                             j += n0 + n1 + 2u;
                         }
-                        p = pp;
+                        pr = prp;
                         k += 4u;
                         st_vol_u32(&sm.produced, k);
                         if ((k & pmask) == 0) { mbar_arrive(&sm.full[steps & smask]); steps++; }
                     }
+                    p = pr + dlt;
                     continue;
                 }
 #endif
