@@ -7,13 +7,16 @@
 // payload lengths of the pair before it (tsq_decode.cpp:68-86), ~50 cycles per pair even from
 // shared memory, and it cannot be split inside a block.  Executed by a whole warp (as in
 // tsq_decode_warp.cu) that chain costs 32 lanes' worth of issue slots per instruction.  Here the
-// chains of up to 31 blocks are walked side by side by the lanes of ONE walker warp -- lane L walks
-// the stream of the CTA's block slot L -- so the serial part costs 1/31 of the issue slots, and it
+// chains of up to 30 blocks are walked side by side by the lanes of the walker warps -- a lane walks
+// the stream of one block slot of the CTA -- so the serial part costs a fraction of the issue slots, and it
 // runs ahead of the copy work instead of alternating with it.  The walker publishes one 8-byte
 // descriptor per pair (stream position of the size byte, output position, the pair's two control
 // bits) into a per-slot shared-memory queue.
 //
-// The copier warp of a slot consumes 16 descriptors (32 symbols) per step, one lane per symbol:
+// The copier warp of a slot consumes one STEP of descriptors at a time.  Two copiers, chosen per block (the walker reads
+// the cadence from the slot): copier_pairs() -- 32 descriptors = 64 symbols per step, lane L owns both symbols of pair L
+// (no-extension format; text-like blocks) -- and copier() -- 16 descriptors = 32 symbols per step, one lane per symbol
+// (extension format; (nearly) incompressible and very compressible blocks).  Either way:
 //   * the compressed stream is staged into a shared-memory ring by 1-D bulk async copies
 //     (cp.async.bulk + mbarrier: TMA without a tensor map; SASS UBLKCP) issued by the copier;
 //   * decoded bytes go to a shared-memory OUTPUT ring first; near matches (distance < ring) read
