@@ -38,6 +38,17 @@ def ctx(torch):
 
 
 @pytest.fixture(scope="module")
+def xctx(torch):
+    """Context of the test-only cross-check library (product objects + the superseded round-1 kernels: encode_impl 2,
+    decode_lanes 1..33).  The product library itself rejects those variants."""
+    import turbosqueeze_b200 as T
+    from turbosqueeze_b200 import api
+    c = T.Context(0, lib=T.library(api.xcheck_library_path()))
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
 def checker(oracle):
     """The compiled unmodified reference when present (multi-threaded), else the C restatement."""
     return Reference() if Reference.available() else oracle
@@ -82,8 +93,10 @@ def golden_input(g):
 
 
 @pytest.mark.parametrize("impl,ext", [(3, 0), (3, 1), (2, 0), (1, 0), (1, 1)], ids=["batch", "batch-ext", "warp", "scalar", "scalar-ext"])
-def test_encode_matches_reference_golden_vectors(torch, ctx, impl, ext):
+def test_encode_matches_reference_golden_vectors(torch, ctx, xctx, impl, ext):
     """tests/golden/golden_blocks.json was produced by the compiled unmodified reference."""
+    if impl == 2:
+        ctx = xctx
     for g in GOLDEN:
         buf = golden_input(g)
         e = g["ext" if ext else "noext"]
@@ -107,7 +120,9 @@ CASES = [(1, 1), (2, 2), (5, 5), (31, 31), (32, 32), (33, 33), (34, 34), (63, 64
 
 @pytest.mark.parametrize("kind", ["text", "random", "rep8", "zeros", "runs"])
 @pytest.mark.parametrize("impl,ext", [(3, 0), (3, 1), (2, 0), (1, 0), (1, 1)], ids=["batch", "batch-ext", "warp", "scalar", "scalar-ext"])
-def test_encode_bit_exact_vs_oracle(torch, ctx, checker, kind, impl, ext):
+def test_encode_bit_exact_vs_oracle(torch, ctx, xctx, checker, kind, impl, ext):
+    if impl == 2:
+        ctx = xctx
     rng = np.random.default_rng(11)
     cases = CASES + [(int(rng.integers(1, 400000)), int(rng.integers(1, 300000))) for _ in range(6)]
     for n, block in cases:
@@ -162,12 +177,15 @@ def test_decode_mixed_blocks_switch_copier_mode(torch, ctx, oracle):
 
 @pytest.mark.parametrize("lanes", [35, 34, 33, 32, 16, 8, 4, 2, 1])
 @pytest.mark.parametrize("ext", [0, 1])
-def test_decode_restores_input(torch, ctx, oracle, lanes, ext):
+def test_decode_restores_input(torch, ctx, xctx, checker, lanes, ext):
     """lanes 34 = walker + copier kernel (tsq_decode_split.cu, lane per symbol), 35 = the same with the lane-per-pair
     copier (64 symbols per step; the extension format runs as 34), 33 = warp-per-block step kernel
     (tsq_decode_warp.cu), 1..32 = sub-warp pair-step kernel."""
     if lanes == 33 and ext:
         pytest.skip("the v1 step kernel is no-extension only")
+    if lanes <= 33:
+        ctx = xctx
+    oracle = checker                      # streams come from the compiled unmodified reference when it travelled with the repo
     ctx.set_option("decode_lanes", lanes)
     try:
         for kind in ("text", "random", "rep8", "zeros", "runs"):
@@ -214,6 +232,20 @@ def test_decode_of_garbage_streams_terminates(torch, ctx, ext):
     out, osz = ctx.decode_blocks(d, len(csz), 65536, ext, comp_sizes=cut)
     torch.cuda.synchronize()
     assert int(osz.sum().item()) == 200000          # the header is reported as it is; the tail of each block is unspecified
+
+
+def test_product_library_has_no_superseded_kernels(torch, ctx):
+    """encode_impl 2 and decode_lanes 1..33 exist only in the cross-check library."""
+    import turbosqueeze_b200 as T
+    buf = W.fill("text", 70000, seed=1)
+    d = torch.from_numpy(buf).cuda()
+    slots, sizes = ctx.encode_blocks(d, 70000, 65536, 0)
+    ctx.set_option("decode_lanes", 16)
+    try:
+        with pytest.raises(T.TsqError):
+            ctx.decode_blocks(slots, sizes.numel(), 65536, 0, comp_sizes=sizes)
+    finally:
+        ctx.set_option("decode_lanes", 0)
 
 
 def test_decode_rejects_oversize_header(torch, ctx):

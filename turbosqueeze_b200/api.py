@@ -15,6 +15,7 @@ BLOCK_MAX = 1 << 22      # TSQ_BLOCK_SZ (reference turbosqueeze.h:38)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
+_libs = {}
 
 _u8p = C.POINTER(C.c_uint8)
 _vp = C.c_void_p
@@ -25,16 +26,25 @@ class TsqError(RuntimeError):
 
 
 def library_path():
-    # TSQB_LIBRARY: development only (scripts/build_variants.sh builds kernel variants for A/B timing)
+    """The product library.  TSQB_LIBRARY (development only: scripts/build_variants.sh builds kernel variants for A/B
+    timing) overrides it; bench.py refuses to run with it set unless told so, and prints the path it loaded."""
     return os.environ.get("TSQB_LIBRARY") or os.path.join(_HERE, "libturbosqueeze_b200.so")
 
 
-def library():
-    """Load libturbosqueeze_b200.so; fails loudly when it has not been built."""
+def xcheck_library_path():
+    """Test-only library: the product's objects plus the superseded round-1 kernels (encode_impl 2, decode_lanes 1..33)."""
+    return os.path.join(os.path.dirname(_HERE), "tests", "xcheck", "libturbosqueeze_b200_xcheck.so")
+
+
+def library(path=None):
+    """Load libturbosqueeze_b200.so (or the library at `path`); fails loudly when it has not been built."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    path = library_path()
+    product = path is None
+    path = path or library_path()
+    if path in _libs:
+        return _libs[path]
     if not os.path.exists(path):
         raise TsqError(f"{path} is missing: the CUDA extension is required (run `make` or __graft_entry__.build()); "
                        "there is no CPU fallback")
@@ -79,7 +89,9 @@ def library():
     L.tsqCompress_MT.restype = C.c_bool
     L.tsqDecompress_MT.argtypes = [_vp, _vp, C.c_size_t, C.c_bool, C.POINTER(_vp), C.POINTER(C.c_size_t), C.c_bool]
     L.tsqDecompress_MT.restype = C.c_bool
-    _lib = L
+    _libs[path] = L
+    if product:
+        _lib = L
     return L
 
 
@@ -92,9 +104,9 @@ def slot_stride(block):
     return int(library().tsqb_slot_stride(block))
 
 
-def _check(status, what):
+def _check(status, what, lib=None):
     if status != 0:
-        raise TsqError(f"{what}: {library().tsqb_last_error().decode()}")
+        raise TsqError(f"{what}: {(lib or library()).tsqb_last_error().decode()}")
 
 
 def _stream_handle(stream):
@@ -113,21 +125,22 @@ def _as_np(data):
 class Context:
     """tsqb_context: one CUDA device + the hash-table scratch of the blocks in flight."""
 
-    def __init__(self, device=0):
-        L = library()
+    def __init__(self, device=0, lib=None):
+        """lib: a library handle from library(path) (tests use the cross-check library); default = the product."""
+        self._L = L = lib or library()
         h = _vp()
-        _check(L.tsqb_create(C.byref(h), int(device)), "tsqb_create")
+        _check(L.tsqb_create(C.byref(h), int(device)), "tsqb_create", L)
         self._h, self.device = h, int(device)
 
     def close(self):
         if getattr(self, "_h", None):
-            library().tsqb_destroy(self._h)
+            self._L.tsqb_destroy(self._h)
             self._h = None
 
     __del__ = close
 
     def set_option(self, key, value):
-        if library().tsqb_set_option(self._h, key.encode(), int(value)) != 0:
+        if self._L.tsqb_set_option(self._h, key.encode(), int(value)) != 0:
             raise TsqError(f"unknown option {key}")
 
     # ---- layer 1: device-resident batch path (torch uint8 CUDA tensors) -------------------------
@@ -142,8 +155,8 @@ class Context:
             slots = torch.zeros(max(nb, 1) * stride, dtype=torch.uint8, device=d_in.device)
         if sizes is None:
             sizes = torch.zeros(max(nb, 1), dtype=torch.int32, device=d_in.device)
-        _check(library().tsqb_encode_blocks(self._h, d_in.data_ptr(), total, block, slots.data_ptr(), stride, sizes.data_ptr(),
-                                            int(ext), _stream_handle(stream)), "tsqb_encode_blocks")
+        _check(self._L.tsqb_encode_blocks(self._h, d_in.data_ptr(), total, block, slots.data_ptr(), stride, sizes.data_ptr(),
+                                            int(ext), _stream_handle(stream)), "tsqb_encode_blocks", self._L)
         return slots, sizes[:nb]
 
     def decode_blocks(self, d_comp, nb, block, ext=0, stride=None, offsets=None, comp_sizes=None, out=None, out_sizes=None,
@@ -155,10 +168,10 @@ class Context:
         if out_sizes is None:
             out_sizes = torch.zeros(max(nb, 1), dtype=torch.int32, device=d_comp.device)
         stride = slot_stride(block) if stride is None else stride
-        _check(library().tsqb_decode_blocks(self._h, d_comp.data_ptr(), offsets.data_ptr() if offsets is not None else None,
+        _check(self._L.tsqb_decode_blocks(self._h, d_comp.data_ptr(), offsets.data_ptr() if offsets is not None else None,
                                             stride if offsets is None else 0,
                                             comp_sizes.data_ptr() if comp_sizes is not None else None, nb, out.data_ptr(), block,
-                                            out_sizes.data_ptr(), int(ext), _stream_handle(stream)), "tsqb_decode_blocks")
+                                            out_sizes.data_ptr(), int(ext), _stream_handle(stream)), "tsqb_decode_blocks", self._L)
         return out, out_sizes[:nb]
 
     def pack_container(self, slots, sizes, block, total, ext=0, stream=None):
@@ -168,8 +181,8 @@ class Context:
         stride = slot_stride(block)
         cont = torch.empty(16 + nb * (stride + 3) + 256, dtype=torch.uint8, device=slots.device)
         n = torch.zeros(1, dtype=torch.int64, device=slots.device)
-        _check(library().tsqb_pack_container(self._h, slots.data_ptr(), stride, sizes.data_ptr(), nb, total, int(ext), cont.data_ptr(),
-                                             n.data_ptr(), _stream_handle(stream)), "tsqb_pack_container")
+        _check(self._L.tsqb_pack_container(self._h, slots.data_ptr(), stride, sizes.data_ptr(), nb, total, int(ext), cont.data_ptr(),
+                                             n.data_ptr(), _stream_handle(stream)), "tsqb_pack_container", self._L)
         return cont, n
 
     def index_container(self, cont, csize, max_blocks, stream=None):
@@ -179,8 +192,8 @@ class Context:
         sizes = torch.zeros(max(max_blocks, 1), dtype=torch.int32, device=dev)
         ext = torch.zeros(max(max_blocks, 1), dtype=torch.int32, device=dev)
         n = torch.zeros(1, dtype=torch.int64, device=dev)
-        _check(library().tsqb_index_container(self._h, cont.data_ptr(), csize, max_blocks, offs.data_ptr(), sizes.data_ptr(),
-                                              ext.data_ptr(), n.data_ptr(), _stream_handle(stream)), "tsqb_index_container")
+        _check(self._L.tsqb_index_container(self._h, cont.data_ptr(), csize, max_blocks, offs.data_ptr(), sizes.data_ptr(),
+                                              ext.data_ptr(), n.data_ptr(), _stream_handle(stream)), "tsqb_index_container", self._L)
         return offs, sizes, ext, n
 
     # ---- host buffers through the device ----------------------------------------------------------
@@ -190,7 +203,7 @@ class Context:
         stride = slot_stride(block)
         slots = np.zeros(max(nb, 1) * stride, dtype=np.uint8)
         sizes = np.zeros(max(nb, 1), dtype=np.uint32)
-        _check(library().tsqb_encode_host(self._h, a.ctypes.data, a.size, block, slots.ctypes.data, sizes.ctypes.data, int(ext)),
+        _check(self._L.tsqb_encode_host(self._h, a.ctypes.data, a.size, block, slots.ctypes.data, sizes.ctypes.data, int(ext)),
                "tsqb_encode_host")
         return slots, sizes[:nb]
 
@@ -198,8 +211,8 @@ class Context:
         out = np.zeros(max(nb, 1) * block, dtype=np.uint8)
         osz = np.zeros(max(nb, 1), dtype=np.uint32)
         cs = np.ascontiguousarray(comp_sizes, dtype=np.uint32) if comp_sizes is not None else None
-        _check(library().tsqb_decode_host(self._h, slots.ctypes.data, stride, cs.ctypes.data if cs is not None else None, nb,
-                                          out.ctypes.data, block, osz.ctypes.data, int(ext)), "tsqb_decode_host")
+        _check(self._L.tsqb_decode_host(self._h, slots.ctypes.data, stride, cs.ctypes.data if cs is not None else None, nb,
+                                          out.ctypes.data, block, osz.ctypes.data, int(ext)), "tsqb_decode_host", self._L)
         return out, osz[:nb]
 
     def compress_buffer(self, data, block=BLOCK_MAX, ext=0, ptr=None, size=None):
@@ -208,7 +221,7 @@ class Context:
             a = _as_np(data)
             ptr, size = a.ctypes.data, a.size
         out, n = _vp(), C.c_uint64(0)
-        _check(library().tsqb_compress_buffer(self._h, ptr, size, block, int(ext), C.byref(out), C.byref(n)), "tsqb_compress_buffer")
+        _check(self._L.tsqb_compress_buffer(self._h, ptr, size, block, int(ext), C.byref(out), C.byref(n)), "tsqb_compress_buffer", self._L)
         try:
             return C.string_at(out, n.value)
         finally:
@@ -217,18 +230,18 @@ class Context:
     def compress_into(self, in_ptr, total, block, ext, out_ptr, out_cap):
         """Host pointer -> TSQ1 container in a caller-owned host buffer; returns its length."""
         n = C.c_uint64(0)
-        _check(library().tsqb_compress_into(self._h, in_ptr, total, block, int(ext), out_ptr, out_cap, C.byref(n)), "tsqb_compress_into")
+        _check(self._L.tsqb_compress_into(self._h, in_ptr, total, block, int(ext), out_ptr, out_cap, C.byref(n)), "tsqb_compress_into", self._L)
         return n.value
 
     def decompress_into(self, in_ptr, in_size, out_ptr, out_cap):
         n = C.c_uint64(0)
-        _check(library().tsqb_decompress_into(self._h, in_ptr, in_size, out_ptr, out_cap, C.byref(n)), "tsqb_decompress_into")
+        _check(self._L.tsqb_decompress_into(self._h, in_ptr, in_size, out_ptr, out_cap, C.byref(n)), "tsqb_decompress_into", self._L)
         return n.value
 
     def decompress_buffer(self, blob):
         a = _as_np(blob)
         out, n = _vp(), C.c_uint64(0)
-        _check(library().tsqb_decompress_buffer(self._h, a.ctypes.data, a.size, C.byref(out), C.byref(n)), "tsqb_decompress_buffer")
+        _check(self._L.tsqb_decompress_buffer(self._h, a.ctypes.data, a.size, C.byref(out), C.byref(n)), "tsqb_decompress_buffer", self._L)
         try:
             return C.string_at(out, n.value)
         finally:

@@ -8,6 +8,8 @@
 #include "tsq_device.cuh"
 
 #include <atomic>
+#include <sys/mman.h>
+#include <unistd.h>
 #include <condition_variable>
 #include <cstdarg>
 #include <deque>
@@ -65,7 +67,11 @@ struct DevBuf {
         p = nullptr; cap = 0;
         const size_t want = (n + (1u << 20)) & ~(size_t)((1u << 20) - 1);
         if (cudaMalloc(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return 1; }
-        if (zero_on_alloc && cudaMemset(p, 0, want) != cudaSuccess) { cudaGetLastError(); cudaFree(p); p = nullptr; return 1; }
+        // The library's streams are non-blocking, so nothing orders a legacy-stream memset before their kernels:
+        // wait for it here (allocations are rare; the epoch scheme relies on "zero = never written").
+        if (zero_on_alloc && (cudaMemset(p, 0, want) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)) {
+            cudaGetLastError(); cudaFree(p); p = nullptr; return 1;
+        }
         cap = want;
         return 0;
     }
@@ -83,7 +89,10 @@ struct tsqb_context {
     int encode_fat = -1;       // batch encoder table format: -1 auto, 0 u16 tables, 1 sector entries
     DevBuf tables;             // hash tables of the blocks in flight (zeroed when allocated: epoch 0 = empty)
     DevBuf ftables;            // batch encoder: 32-byte entries, only ever written by that kernel, zeroed at allocation
-    uint64_t launch_id = 0;    // encode launches so far: the epoch of the batch encoder's table entries
+    uint64_t launch_id = 1u << 12;  // encode launches so far: the epoch of the batch encoder's table entries.  Starts high enough
+                               // that (epoch >> 32) is never 0: a half-zeroed sector can never pass for a live entry
+    cudaEvent_t ev_scratch = nullptr;   // last launch that used the context's shared scratch (tables, pack offsets)
+    bool scratch_busy = false;
     // staging for the host-buffer entry points
     DevBuf in, slots, sizes, out, osizes, cont, offs, ext, misc;
     cudaStream_t stream = nullptr;
@@ -96,7 +105,7 @@ struct tsqb_context {
     uint64_t* h_len = nullptr;                 // pinned: per-chunk container length
     int pipeline = 1;                          // 0: one-shot staging (round-1 v1 behaviour)
     uint64_t pipeline_min = 64ull << 20;       // buffers below this many bytes are staged in one shot
-    std::mutex mtx;
+    std::recursive_mutex mtx;          // host entry points hold it across their layer-1 calls
 };
 
 extern "C" int tsqb_create(tsqb_context** out, int device)
@@ -116,7 +125,8 @@ extern "C" int tsqb_create(tsqb_context** out, int device)
     bool ok = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->s_in, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->s_out, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaMallocHost((void**)&c->h_len, sizeof(uint64_t) * tsqb_context::kPipe) == cudaSuccess;
+              cudaMallocHost((void**)&c->h_len, sizeof(uint64_t) * tsqb_context::kPipe) == cudaSuccess &&
+              cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming) == cudaSuccess;
     for (int k = 0; ok && k < tsqb_context::kPipe; k++)
         ok = cudaStreamCreateWithFlags(&c->s_chunk[k], cudaStreamNonBlocking) == cudaSuccess &&
              cudaEventCreateWithFlags(&c->ev_in[k], cudaEventDisableTiming) == cudaSuccess &&
@@ -147,6 +157,7 @@ extern "C" void tsqb_destroy(tsqb_context* c)
         if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
     }
     if (c->h_len) cudaFreeHost(c->h_len);
+    if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
     delete c;
 }
 
@@ -177,6 +188,24 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
 }
 
 // ------------------------------------------------------------------------------ layer 1: device path
+// Layer 1 may be called from several threads and on several streams with one context, but the context's scratch (hash
+// tables, pack offsets, the epoch counter) is shared: a launch takes c->mtx for its set-up, makes its stream wait for
+// the previous user of the scratch (an event), launches, and records the event again.  Launches on different streams
+// are therefore serialised on the device where they share tables -- never interleaved.  Launches that bring their own
+// table region (`tables`, the pipelined host path) skip the wait.
+static int scratch_acquire(tsqb_context* c, cudaStream_t st)
+{
+    if (c->scratch_busy) CU(cudaStreamWaitEvent(st, c->ev_scratch, 0));
+    return 0;
+}
+
+static int scratch_release(tsqb_context* c, cudaStream_t st)
+{
+    CU(cudaEventRecord(c->ev_scratch, st));
+    c->scratch_busy = true;
+    return 0;
+}
+
 // `tables` (optional): caller-provided region of encode_slots_for(...) tables, for launches that overlap in time
 static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t total, uint32_t block, uint8_t* d_slots,
                               uint64_t stride, uint32_t* d_sizes, uint32_t* d_tailflags, uint32_t with_ext, void* stream,
@@ -187,6 +216,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     if (stride < tsqb_slot_stride(block)) return fail("tsqb_encode_blocks: slot stride %llu < %llu", (unsigned long long)stride,
                                                       (unsigned long long)tsqb_slot_stride(block));
     if (total == 0) return 0;
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
     EncodeArgs a;
     a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
@@ -198,11 +228,22 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.fat = (c->encode_fat < 0 ? encode_wants_fat(impl, a.n_slots) : (impl == 3 && c->encode_fat != 0)) ? 1u : 0u;
     if (tables) { a.tables = tables; a.fat = impl == 3 ? 1u : 0u; }            // the pipelined path provisions sector tables
     else {
+        // The tables of all blocks in flight: up to sm_count * 32 x 4 MiB = 18.5 GiB.  On a GPU that cannot give that
+        // much (shared, or smaller), run with fewer blocks in flight instead of failing: halve until it fits.
         DevBuf& tb = a.fat ? c->ftables : c->tables;
-        if (tb.ensure((size_t)a.n_slots * encode_table_bytes(impl, a.fat != 0))) return fail("tsqb_encode_blocks: cannot allocate %u hash tables", a.n_slots);
+        for (;;) {
+            const size_t need = (size_t)a.n_slots * encode_table_bytes(impl, a.fat != 0);
+            size_t free_b = 0, total_b = 0;
+            const bool fits = need <= tb.cap || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || need + (256u << 20) <= free_b + tb.cap;
+            if (fits && tb.ensure(need) == 0) break;
+            if (a.n_slots <= 1) return fail("tsqb_encode_blocks: cannot allocate a hash table (%zu bytes)", need);
+            a.n_slots = (a.n_slots + 1) / 2;
+        }
         a.tables = (uint16_t*)tb.p;
+        if (scratch_acquire(c, (cudaStream_t)stream)) return 1;
     }
     CU(launch_encode(a, impl, with_ext != 0, c->sm_count, (cudaStream_t)stream));
+    if (!tables && scratch_release(c, (cudaStream_t)stream)) return 1;
     g_launches += 1;
     return 0;
 }
@@ -235,10 +276,14 @@ extern "C" int tsqb_pack_container(tsqb_context* c, const uint8_t* d_slots, uint
                                    uint64_t* d_total_out, void* stream)
 {
     if (!c) return fail("tsqb_pack_container: null context");
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
+    if (c->offs.cap < (nb + 1) * sizeof(uint64_t) && c->scratch_busy) CU(cudaEventSynchronize(c->ev_scratch));   // about to be re-allocated
     if (c->offs.ensure((nb + 1) * sizeof(uint64_t))) return fail("tsqb_pack_container: out of device memory");
+    if (scratch_acquire(c, (cudaStream_t)stream)) return 1;
     CU(launch_pack(d_slots, stride, d_sizes, nb, total_u, with_ext, d_container, d_total_out, (uint64_t*)c->offs.p,
                    (cudaStream_t)stream));
+    if (scratch_release(c, (cudaStream_t)stream)) return 1;
     g_launches += nb ? 2 : 1;
     return 0;
 }
@@ -271,7 +316,7 @@ extern "C" int tsqb_encode_host(tsqb_context* c, const uint8_t* in, uint64_t tot
     if (!c) return fail("tsqb_encode_host: null context");
     if (block == 0 || block > kBlockMax) return fail("tsqb_encode_host: bad block size %u", block);
     if (total == 0) return 0;
-    std::lock_guard<std::mutex> lk(c->mtx);
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
     if (stage_input(c, in, total, nullptr, 0)) return 1;
@@ -280,9 +325,10 @@ extern "C" int tsqb_encode_host(tsqb_context* c, const uint8_t* in, uint64_t tot
     if (tsqb_encode_blocks(c, (uint8_t*)c->in.p, total, block, (uint8_t*)c->slots.p, stride, (uint32_t*)c->sizes.p, with_ext, c->stream)) return 1;
     CU(cudaMemcpyAsync(sizes, c->sizes.p, nb * 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    // only the used bytes of every slot travel back
-    for (uint64_t b = 0; b < nb; b++)
-        CU(cudaMemcpyAsync(slots + b * stride, (uint8_t*)c->slots.p + b * stride, sizes[b], cudaMemcpyDeviceToHost, c->stream));
+    // only the used part of the slots travels back: ONE strided copy, as wide as the largest stream
+    uint32_t widest = 0;
+    for (uint64_t b = 0; b < nb; b++) if (sizes[b] > widest) widest = sizes[b];
+    if (widest) CU(cudaMemcpy2DAsync(slots, stride, c->slots.p, stride, widest, nb, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -292,14 +338,15 @@ extern "C" int tsqb_decode_host(tsqb_context* c, const uint8_t* slots, uint64_t 
 {
     if (!c) return fail("tsqb_decode_host: null context");
     if (nb == 0) return 0;
-    std::lock_guard<std::mutex> lk(c->mtx);
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
     if (c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4) || c->out.ensure(nb * out_stride) || c->osizes.ensure(nb * 4))
         return fail("tsqb_decode_host: out of device memory");
     if (comp_sizes) {
-        for (uint64_t b = 0; b < nb; b++)
-            CU(cudaMemcpyAsync((uint8_t*)c->slots.p + b * stride, slots + b * stride, comp_sizes[b] < stride ? comp_sizes[b] : stride,
-                               cudaMemcpyHostToDevice, c->stream));
+        uint64_t widest = 0;
+        for (uint64_t b = 0; b < nb; b++) if (comp_sizes[b] > widest) widest = comp_sizes[b];
+        if (widest > stride) widest = stride;
+        if (widest) CU(cudaMemcpy2DAsync(c->slots.p, stride, slots, stride, widest, nb, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(c->sizes.p, comp_sizes, nb * 4, cudaMemcpyHostToDevice, c->stream));
     } else {
         CU(cudaMemcpyAsync(c->slots.p, slots, nb * stride, cudaMemcpyHostToDevice, c->stream));
@@ -314,10 +361,19 @@ extern "C" int tsqb_decode_host(tsqb_context* c, const uint8_t* slots, uint64_t 
     return 0;
 }
 
+// Per-block progress of a host-path job (tsq_threads.cpp:248-254, :654-655: the reference's writer thread reports
+// (blocks written) / n_blocks after every block).  Called on the thread that runs the job, in block order.
+typedef std::function<void(uint64_t blocks_done, uint64_t n_blocks)> ProgressFn;
+static void report_blocks(const ProgressFn* prog, uint64_t from, uint64_t to, uint64_t nb)
+{
+    if (prog && *prog) for (uint64_t b = from; b < to; b++) (*prog)(b + 1, nb);
+}
+
 // `tail`: see stage_input.  Container is assembled on the device and comes back in one copy, either
 // into a fresh malloc (host_out == nullptr) or into the caller's buffer of `host_cap` bytes.
 static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
-                           uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size)
+                           uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size,
+                           const ProgressFn* prog = nullptr)
 {
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
     if (stage_input(c, in, total, tail, tail_n)) return 1;
@@ -339,8 +395,13 @@ static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, c
     } else if (clen > host_cap) {
         return fail("compress: output needs %llu bytes, caller gave %llu", (unsigned long long)clen, (unsigned long long)host_cap);
     }
-    CU(cudaMemcpyAsync(host, c->cont.p, clen, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    cudaError_t e = cudaMemcpyAsync(host, c->cont.p, clen, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) {
+        if (!host_out) free(host);
+        return fail("compress: %s", cudaGetErrorString(e));
+    }
+    report_blocks(prog, 0, nb, nb);
     if (out) *out = host;
     *out_size = clen;
     return 0;
@@ -355,7 +416,8 @@ static int compress_locked(tsqb_context* c, const uint8_t* in, uint64_t total, c
 // flight; every chunk therefore gets its own hash-table region.
 
 static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
-                              uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size)
+                              uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size,
+                              const ProgressFn* prog = nullptr)
 {
     constexpr int KMAX = tsqb_context::kPipe;
     const int K = c->pipe_chunks;
@@ -397,30 +459,37 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
         c->cont.ensure(ccap * nchunks) || c->offs.ensure((nb + KMAX) * 8) || c->misc.ensure(64 * KMAX) || (impl == 3 ? c->ftables : c->tables).ensure(tab_total * encode_table_bytes(impl, true)))
         return fail("compress: out of device memory");
+    // an error after the first chunk is in flight: let the device finish before the context's buffers are touched again
+#define CUP(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) { cudaDeviceSynchronize(); return fail("%s: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
     uint8_t* d_in = (uint8_t*)c->in.p;
-    CU(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
-    if (tail && tail_n) CU(cudaMemcpyAsync(d_in + total, tail, tail_n, cudaMemcpyHostToDevice, c->s_in));
+    CUP(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
+    if (tail && tail_n) CUP(cudaMemcpyAsync(d_in + total, tail, tail_n, cudaMemcpyHostToDevice, c->s_in));
     for (int k = 0; k < nchunks; k++) {
         const uint64_t b0 = cb[k], b1 = cb[k + 1];
         const uint64_t lo = b0 * block, hi = (b1 * block < total) ? b1 * block : total;
         // the last block of the chunk reads a few bytes past it (tsq_encode.cpp:74,126-128): ship them with this chunk
         const uint64_t hi_tail = (hi + TSQB_INPUT_PAD < total) ? hi + TSQB_INPUT_PAD : total;
-        CU(cudaMemcpyAsync(d_in + lo, in + lo, hi_tail - lo, cudaMemcpyHostToDevice, c->s_in));
-        CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        CUP(cudaMemcpyAsync(d_in + lo, in + lo, hi_tail - lo, cudaMemcpyHostToDevice, c->s_in));
+        CUP(cudaEventRecord(c->ev_in[k], c->s_in));
         cudaStream_t st = c->s_chunk[k];
-        CU(cudaStreamWaitEvent(st, c->ev_in[k], 0));
-        CU(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
+        CUP(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+        CUP(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
         // a chunk is encoded as a buffer of its own: (hi - lo) bytes that happen to be followed by the next chunk
         if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr,
-                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)), slot_cap[k])) return 1;
+                               with_ext, st, (uint16_t*)((uint8_t*)(impl == 3 ? c->ftables : c->tables).p + tab_at[k] * encode_table_bytes(impl, true)), slot_cap[k])) { cudaDeviceSynchronize(); return 1; }
         uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
         uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
-        CU(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,
+        CUP(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,
                        (uint64_t*)c->offs.p + b0 + k, st));
         g_launches += 2;
-        CU(cudaMemcpyAsync(&c->h_len[k], d_len, 8, cudaMemcpyDeviceToHost, st));
-        CU(cudaEventRecord(c->ev_done[k], st));
+        CUP(cudaMemcpyAsync(&c->h_len[k], d_len, 8, cudaMemcpyDeviceToHost, st));
+        CUP(cudaEventRecord(c->ev_done[k], st));
     }
+#undef CUP
     // results leave in order; the body of chunk k goes behind the bodies before it
     uint8_t* host = host_out;
     if (!host) {                                                              // malloc mode: the size is known last -> worst case
@@ -437,6 +506,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
         if (host_out && at + body > host_cap) { too_small = true; break; }
         err = cudaMemcpyAsync(host + at, (uint8_t*)c->cont.p + (uint64_t)k * ccap + 16, body, cudaMemcpyDeviceToHost, c->s_out);
         at += body;
+        report_blocks(prog, cb[k], k + 1 == nchunks ? nb - 1 : cb[k + 1], nb);   // the last block is reported when everything is home
     }
     if (err == cudaSuccess) err = cudaStreamSynchronize(c->s_out);
     if (err != cudaSuccess || too_small) {
@@ -449,6 +519,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     const uint32_t nb32 = (uint32_t)nb;
     memcpy(host + 4, &nb32, 4);
     memcpy(host + 8, &total, 8);
+    if (nb) report_blocks(prog, nb - 1, nb, nb);
     if (out) *out = host;
     *out_size = at;
     return 0;
@@ -459,7 +530,7 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
 // copied back on separate streams.  Returns 1 with g_err set on failure, -1 when the container is not
 // regular (mixed block sizes / flags): the caller then falls back to the one-shot path.
 static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* host_out, uint64_t host_cap,
-                                uint8_t** out, uint64_t* out_size)
+                                uint8_t** out, uint64_t* out_size, const ProgressFn* prog = nullptr)
 {
     const int K = c->pipe_chunks;
     std::vector<uint64_t> offs;
@@ -467,6 +538,7 @@ static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_
     uint32_t with_ext = 0, block = 0;
     uint64_t total = 0;
     uint32_t nb_hdr;
+    bool short_seen = false;                                                  // a block shorter than the first one: must be the last
     memcpy(&nb_hdr, in + 4, 4);                                               // tsq_threads.cpp:728-757 reads this many blocks
     for (uint64_t at = 16; at + 3 <= in_size && offs.size() < nb_hdr;) {
         uint32_t len = (uint32_t)in[at] | ((uint32_t)in[at + 1] << 8) | ((uint32_t)in[at + 2] << 16);
@@ -477,7 +549,10 @@ static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_
         const uint32_t u = (uint32_t)h[0] | ((uint32_t)h[1] << 8) | ((uint32_t)h[2] << 16);
         if (offs.empty()) { with_ext = ext; block = u; }
         else if (ext != with_ext) return -1;
-        if (u > kBlockMax || u > block || (total % (block ? block : 1)) != 0) return -1;   // only the last block may be short
+        // Block b is decoded to b * block and the output copied back as one range: every block but the last must
+        // decode to exactly `block` bytes (a 0-byte or short block in the middle goes to the one-shot path)
+        if (short_seen || u > kBlockMax || u > block) return -1;
+        if (u != block) short_seen = true;
         offs.push_back(at + 3); sizes.push_back(len);
         total += u;
         at += 3 + (uint64_t)len;
@@ -491,31 +566,55 @@ static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_
     } else if (total > host_cap) {
         return fail("decompress: output needs %llu bytes, caller gave %llu", (unsigned long long)total, (unsigned long long)host_cap);
     }
+    // any failure from here on: wait for the streams that still use the context's buffers, release the output
+    auto bail = [&](int rc) { cudaDeviceSynchronize(); if (!host_out) free(host); return rc; };
+#define CUP(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) { fail("%s: %s", #call, cudaGetErrorString(e_)); return bail(1); }  \
+    } while (0)
     if (c->cont.ensure(in_size + 512) || c->offs.ensure(nb * 8) || c->sizes.ensure(nb * 4) || c->osizes.ensure(nb * 4) ||
-        c->out.ensure(nb * (uint64_t)block))
-        return fail("decompress: out of device memory");
-    CU(cudaMemcpyAsync(c->offs.p, offs.data(), nb * 8, cudaMemcpyHostToDevice, c->s_in));
-    CU(cudaMemcpyAsync(c->sizes.p, sizes.data(), nb * 4, cudaMemcpyHostToDevice, c->s_in));
+        c->out.ensure(nb * (uint64_t)block)) { fail("decompress: out of device memory"); return bail(1); }
+    CUP(cudaMemcpyAsync(c->offs.p, offs.data(), nb * 8, cudaMemcpyHostToDevice, c->s_in));
+    CUP(cudaMemcpyAsync(c->sizes.p, sizes.data(), nb * 4, cudaMemcpyHostToDevice, c->s_in));
     const uint64_t per = (nb + K - 1) / K;
     const int nchunks = (int)((nb + per - 1) / per);
     for (int k = 0; k < nchunks; k++) {
         const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
         const uint64_t lo = offs[b0], hi = offs[b1 - 1] + sizes[b1 - 1];
-        CU(cudaMemcpyAsync((uint8_t*)c->cont.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->s_in));
-        CU(cudaEventRecord(c->ev_in[k], c->s_in));
+        CUP(cudaMemcpyAsync((uint8_t*)c->cont.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->s_in));
+        CUP(cudaEventRecord(c->ev_in[k], c->s_in));
         cudaStream_t st = c->s_chunk[k];
-        CU(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+        CUP(cudaStreamWaitEvent(st, c->ev_in[k], 0));
         if (tsqb_decode_blocks(c, (uint8_t*)c->cont.p, (uint64_t*)c->offs.p + b0, 0, (uint32_t*)c->sizes.p + b0, b1 - b0,
-                               (uint8_t*)c->out.p + b0 * (uint64_t)block, block, (uint32_t*)c->osizes.p + b0, with_ext, st)) return 1;
-        CU(cudaEventRecord(c->ev_done[k], st));
-        CU(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
+                               (uint8_t*)c->out.p + b0 * (uint64_t)block, block, (uint32_t*)c->osizes.p + b0, with_ext, st)) return bail(1);
+        CUP(cudaEventRecord(c->ev_done[k], st));
+        CUP(cudaStreamWaitEvent(c->s_out, c->ev_done[k], 0));
         const uint64_t olo = b0 * (uint64_t)block, ohi = (b1 * (uint64_t)block < total) ? b1 * (uint64_t)block : total;
-        CU(cudaMemcpyAsync(host + olo, (uint8_t*)c->out.p + olo, ohi - olo, cudaMemcpyDeviceToHost, c->s_out));
+        CUP(cudaMemcpyAsync(host + olo, (uint8_t*)c->out.p + olo, ohi - olo, cudaMemcpyDeviceToHost, c->s_out));
+        CUP(cudaEventRecord(c->ev_in[k], c->s_out));                          // reused: chunk k's bytes are home
     }
-    CU(cudaStreamSynchronize(c->s_out));
+    for (int k = 0; k < nchunks; k++) {                                       // progress, chunk by chunk as the output lands
+        CUP(cudaEventSynchronize(c->ev_in[k]));
+        report_blocks(prog, k * per, ((k + 1) * per < nb) ? (k + 1) * per : nb, nb);
+    }
+    CUP(cudaStreamSynchronize(c->s_out));
+#undef CUP
     if (out) *out = host;
     *out_size = total;
     return 0;
+}
+
+// One host buffer -> one TSQ1 container (pipelined above pipeline_min bytes).  `tail`: the bytes that follow the input in
+// the caller's memory (the reference's memory path encodes in place and its last block reads them, tsq_threads.cpp:109).
+static int compress_any(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
+                        uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size, const ProgressFn* prog)
+{
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    if (c->pipeline && total >= c->pipeline_min)
+        return compress_pipelined(c, in, total, tail, tail_n, block, with_ext, host_out, host_cap, out, out_size, prog);
+    return compress_locked(c, in, total, tail, tail_n, block, with_ext, host_out, host_cap, out, out_size, prog);
 }
 
 extern "C" int tsqb_compress_buffer(tsqb_context* c, const uint8_t* in, uint64_t total, uint32_t block, uint32_t with_ext,
@@ -523,10 +622,7 @@ extern "C" int tsqb_compress_buffer(tsqb_context* c, const uint8_t* in, uint64_t
 {
     if (!c || !out || !out_size) return fail("tsqb_compress_buffer: null argument");
     if (block == 0 || block > kBlockMax) return fail("tsqb_compress_buffer: bad block size %u", block);
-    std::lock_guard<std::mutex> lk(c->mtx);
-    CU(cudaSetDevice(c->device));
-    if (c->pipeline && total >= c->pipeline_min) return compress_pipelined(c, in, total, nullptr, 0, block, with_ext, nullptr, 0, out, out_size);
-    return compress_locked(c, in, total, nullptr, 0, block, with_ext, nullptr, 0, out, out_size);
+    return compress_any(c, in, total, nullptr, 0, block, with_ext, nullptr, 0, out, out_size, nullptr);
 }
 
 extern "C" int tsqb_compress_into(tsqb_context* c, const uint8_t* in, uint64_t total, uint32_t block, uint32_t with_ext,
@@ -534,14 +630,11 @@ extern "C" int tsqb_compress_into(tsqb_context* c, const uint8_t* in, uint64_t t
 {
     if (!c || !out || !out_size) return fail("tsqb_compress_into: null argument");
     if (block == 0 || block > kBlockMax) return fail("tsqb_compress_into: bad block size %u", block);
-    std::lock_guard<std::mutex> lk(c->mtx);
-    CU(cudaSetDevice(c->device));
-    if (c->pipeline && total >= c->pipeline_min) return compress_pipelined(c, in, total, nullptr, 0, block, with_ext, out, out_capacity, nullptr, out_size);
-    return compress_locked(c, in, total, nullptr, 0, block, with_ext, out, out_capacity, nullptr, out_size);
+    return compress_any(c, in, total, nullptr, 0, block, with_ext, out, out_capacity, nullptr, out_size, nullptr);
 }
 
 static int decompress_locked(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* host_out, uint64_t host_cap,
-                             uint8_t** out, uint64_t* out_size)
+                             uint8_t** out, uint64_t* out_size, const ProgressFn* prog = nullptr)
 {
     uint32_t nb_hdr; uint64_t total_hdr;
     memcpy(&nb_hdr, in + 4, 4); memcpy(&total_hdr, in + 8, 8);
@@ -592,33 +685,45 @@ static int decompress_locked(tsqb_context* c, const uint8_t* in, uint64_t in_siz
     } else if (total > host_cap) {
         return fail("decompress: output needs %llu bytes, caller gave %llu", (unsigned long long)total, (unsigned long long)host_cap);
     }
+    cudaError_t e = cudaSuccess;
     if (packed) {
-        if (total) CU(cudaMemcpyAsync(host, c->out.p, total, cudaMemcpyDeviceToHost, c->stream));
+        if (total) e = cudaMemcpyAsync(host, c->out.p, total, cudaMemcpyDeviceToHost, c->stream);
     } else {
         uint64_t at = 0;
-        for (uint64_t b = 0; b < nb; b++) {
-            if (osz[b]) CU(cudaMemcpyAsync(host + at, (uint8_t*)c->out.p + b * ostride, osz[b], cudaMemcpyDeviceToHost, c->stream));
+        for (uint64_t b = 0; b < nb && e == cudaSuccess; b++) {
+            if (osz[b]) e = cudaMemcpyAsync(host + at, (uint8_t*)c->out.p + b * ostride, osz[b], cudaMemcpyDeviceToHost, c->stream);
             at += osz[b];
         }
     }
-    CU(cudaStreamSynchronize(c->stream));
+    const cudaError_t e2 = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess || e2 != cudaSuccess) {
+        if (!host_out) free(host);
+        return fail("decompress: %s", cudaGetErrorString(e != cudaSuccess ? e : e2));
+    }
+    report_blocks(prog, 0, nb, nb);
     if (out) *out = host;
     *out_size = total;
     (void)total_hdr;
     return 0;
 }
 
+static int decompress_any(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* host_out, uint64_t host_cap, uint8_t** out,
+                          uint64_t* out_size, const ProgressFn* prog)
+{
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    CU(cudaSetDevice(c->device));
+    if (c->pipeline && in_size >= c->pipeline_min) {
+        const int r = decompress_pipelined(c, in, in_size, host_out, host_cap, out, out_size, prog);
+        if (r >= 0) return r;
+    }
+    return decompress_locked(c, in, in_size, host_out, host_cap, out, out_size, prog);
+}
+
 extern "C" int tsqb_decompress_buffer(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t** out, uint64_t* out_size)
 {
     if (!c || !in || !out || !out_size) return fail("tsqb_decompress_buffer: null argument");
     if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_buffer: not a TSQ1 container");
-    std::lock_guard<std::mutex> lk(c->mtx);
-    CU(cudaSetDevice(c->device));
-    if (c->pipeline && in_size >= c->pipeline_min) {
-        const int r = decompress_pipelined(c, in, in_size, nullptr, 0, out, out_size);
-        if (r >= 0) return r;
-    }
-    return decompress_locked(c, in, in_size, nullptr, 0, out, out_size);
+    return decompress_any(c, in, in_size, nullptr, 0, out, out_size, nullptr);
 }
 
 extern "C" int tsqb_decompress_into(tsqb_context* c, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_capacity,
@@ -626,13 +731,7 @@ extern "C" int tsqb_decompress_into(tsqb_context* c, const uint8_t* in, uint64_t
 {
     if (!c || !in || !out || !out_size) return fail("tsqb_decompress_into: null argument");
     if (in_size < 16 || memcmp(in, "TSQ1", 4) != 0) return fail("tsqb_decompress_into: not a TSQ1 container");
-    std::lock_guard<std::mutex> lk(c->mtx);
-    CU(cudaSetDevice(c->device));
-    if (c->pipeline && in_size >= c->pipeline_min) {
-        const int r = decompress_pipelined(c, in, in_size, out, out_capacity, nullptr, out_size);
-        if (r >= 0) return r;
-    }
-    return decompress_locked(c, in, in_size, out, out_capacity, nullptr, out_size);
+    return decompress_any(c, in, in_size, out, out_capacity, nullptr, out_size, nullptr);
 }
 
 // ------------------------------------------------------------- layer 2: the reference's entry points
@@ -688,11 +787,20 @@ extern "C" void tsqInit(struct TSQCompressionContext* ctx)          // tsq_conte
 extern "C" void tsqEncode(struct TSQCompressionContext* ctx, uint8_t* in, uint8_t* out, uint32_t* outputSize, uint32_t inputSize,
                           uint32_t withExtensions)
 {
-    (void)ctx;
     if (outputSize) *outputSize = 0;
     tsqb_context* c = default_context();
     if (!c || !in || !out || !outputSize || inputSize == 0 || inputSize > kBlockMax) return;
-    std::lock_guard<std::mutex> lk(c->mtx);
+    // Documented divergence: the device path DEFINES the table as zero at entry (every reference caller runs tsqInit or
+    // memsets refhash first).  A caller that skips that would get different bytes from the reference: say so, once.
+    if (ctx && ctx->refhash) {
+        static std::atomic<bool> warned{false};
+        const uint64_t* w = reinterpret_cast<const uint64_t*>(ctx->refhash);
+        uint64_t any = 0;
+        for (size_t q = 0; q < TSQB_HASH_BYTES / 8; q++) any |= w[q];
+        if (any && !warned.exchange(true))
+            fprintf(stderr, "turbosqueeze_b200: tsqEncode called with a non-zero refhash table; the device path encodes as if tsqInit had been called\n");
+    }
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
     const uint64_t stride = tsqb_slot_stride(inputSize);
     // the reference reads <= 19 bytes past the block (72 with extensions): ship exactly those
     const uint32_t tail_n = withExtensions ? 72u : 19u;
@@ -724,6 +832,8 @@ bad:
     fprintf(stderr, "turbosqueeze_b200: tsqEncode failed: %s\n", tsqb_last_error());
 }
 
+static uint64_t stream_extent(const uint8_t* in, uint32_t size, bool ext);
+
 extern "C" void tsqDecode(uint8_t* in, uint8_t* out, uint32_t* outputSize, uint32_t inputSize, uint32_t withExtensions)
 {
     if (outputSize) *outputSize = 0;
@@ -731,9 +841,10 @@ extern "C" void tsqDecode(uint8_t* in, uint8_t* out, uint32_t* outputSize, uint3
     if (!c || !in || !out || !outputSize) return;
     const uint32_t size = (uint32_t)in[0] | ((uint32_t)in[1] << 8) | ((uint32_t)in[2] << 16);
     if (size > kBlockMax) return;                                    // tsq_decode.cpp:53
-    std::lock_guard<std::mutex> lk(c->mtx);
-    // the reference ignores inputSize (tsq_decode.cpp:42-126); without it the worst case is shipped
-    uint64_t n_in = inputSize ? inputSize : tsqb_slot_stride(size);
+    std::lock_guard<std::recursive_mutex> lk(c->mtx);
+    // the reference ignores inputSize (tsq_decode.cpp:42-126); without it the stream is measured by its own size bytes,
+    // so that nothing behind the stream is read from the caller's buffer
+    uint64_t n_in = inputSize ? inputSize : stream_extent(in, size, withExtensions != 0);
     if (cudaSetDevice(c->device) != cudaSuccess) goto bad;
     if (c->slots.ensure(n_in + 512) || c->sizes.ensure(4) || c->out.ensure((uint64_t)size + 16) || c->osizes.ensure(4)) goto bad;
     if (cudaMemsetAsync((uint8_t*)c->slots.p + n_in, 0, 512, c->stream) != cudaSuccess) goto bad;
@@ -751,6 +862,29 @@ extern "C" void tsqDecode(uint8_t* in, uint8_t* out, uint32_t* outputSize, uint3
 bad:
     cudaGetLastError();
     fprintf(stderr, "turbosqueeze_b200: tsqDecode failed: %s\n", tsqb_last_error());
+}
+
+// Length of a block's token stream, found the way the reference's decoder finds it: by walking the control and size
+// bytes (tsq_decode.cpp:60-123; :137-314 with extensions).  Touches exactly the bytes the reference would read, never
+// one past them, and copies nothing.  Used only when the caller passes inputSize == 0 (the reference ignores inputSize).
+static uint64_t stream_extent(const uint8_t* in, uint32_t size, bool ext)
+{
+    uint64_t i = 3;
+    uint32_t j = 0;
+    while (j < size) {
+        const uint32_t ctl = in[i++];
+        for (int p = 0; p < 4 && j < size; p++) {
+            const uint32_t nib = in[i++];
+            const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+            const bool l0 = (ctl & (0x80u >> (2 * p))) != 0, l1 = (ctl & (0x40u >> (2 * p))) != 0;
+            i += l0 ? n0 + 1u : 2u;
+            j += (ext && !l0 && n0 < 3u) ? 16u * (n0 + 2u) : n0 + 1u;
+            if (j >= size) break;                                    // the second symbol is padding: nothing of it is read
+            i += l1 ? n1 + 1u : 2u;
+            j += (ext && !l1 && n1 < 3u) ? 16u * (n1 + 2u) : n1 + 1u;
+        }
+    }
+    return i;
 }
 
 static bool read_all(FILE* f, std::vector<uint8_t>& v)
@@ -799,58 +933,122 @@ extern "C" void tsqDecompress(FILE* in, FILE* out)
     free(blob);
 }
 
-// ---- buffer API (tsq_threads.cpp:278-441, :679-890)
-// The reference's contexts are thread pools; here a context is a device context plus ONE job thread that runs
-// the queued jobs in order and invokes their callbacks (the reference's callbacks run on its writer thread).
+// ---- buffer API and asynchronous job API (tsq_threads.cpp:278-441, :679-890)
+// The reference pushes the blocks of consecutive jobs through one pipeline of reader / worker / writer threads
+// (tsq_threads.cpp:52-275): jobs overlap in flight, and results and callbacks leave strictly in submission order on the
+// writer thread (:199,:611) -- one progress callback per written block (:248-254,:654-655), then the completion
+// callback (:256-268).  Here a context owns kLanes job threads, each with a device context of its own (streams +
+// scratch), which take jobs from one queue and run them concurrently on the GPU.  The CALLBACKS are delivered in
+// submission order: what a job reports while an older job is still unfinished is held back until it is the oldest.
 namespace {
-struct JobThread {
-    std::mutex m;
+struct JobEngine {
+    static constexpr int kLanes = 2;
+    struct Job {
+        uint32_t id = 0;
+        uint64_t seq = 0;
+        std::function<bool(tsqb_context*, const ProgressFn*)> run;        // the device work; true = success
+        std::function<void(uint32_t, bool)> completion_cb;
+        std::function<void(uint32_t, double)> progress_cb;
+    };
+
+    std::mutex m;                       // queue
     std::condition_variable cv;
-    std::deque<std::function<void()>> jobs;
-    bool stop = false;
+    std::deque<Job> jobs;
+    bool stop = false, lane0_busy = false;
     uint32_t next_id = 1;
-    std::thread th;
-    JobThread() : th([this] { run(); }) {}
-    ~JobThread()                                                     // drains: tsq_context.cpp:150-155 waits for in-flight jobs
+    uint64_t next_seq = 0;
+    std::mutex dm;                      // ordered delivery of callbacks
+    std::condition_variable dcv;
+    uint64_t head_seq = 0;              // oldest job whose completion callback has not run yet
+    tsqb_context* dev[kLanes] = {};
+    std::thread th[kLanes];
+
+    explicit JobEngine(tsqb_context* dev0)
+    {
+        dev[0] = dev0;
+        for (int l = 0; l < kLanes; l++) th[l] = std::thread([this, l] { lane_main(l); });
+    }
+    ~JobEngine()                        // drains: tsq_context.cpp:150-155 waits for the jobs in flight
     {
         { std::lock_guard<std::mutex> lk(m); stop = true; }
         cv.notify_all();
-        th.join();
+        for (int l = 0; l < kLanes; l++) th[l].join();
+        for (int l = 1; l < kLanes; l++) if (dev[l]) tsqb_destroy(dev[l]);
     }
-    uint32_t submit(std::function<void(uint32_t)> job)
+    uint32_t submit(Job j)
     {
         std::lock_guard<std::mutex> lk(m);
-        const uint32_t id = next_id++;
+        j.id = next_id++;
         if (next_id == 0) next_id = 1;
-        jobs.emplace_back([job, id] { job(id); });
-        cv.notify_one();
+        j.seq = next_seq++;
+        const uint32_t id = j.id;
+        jobs.push_back(std::move(j));
+        cv.notify_all();
         return id;
     }
-    void run()
+    void lane_main(int lane)
     {
         for (;;) {
-            std::function<void()> j;
+            Job j;
             {
                 std::unique_lock<std::mutex> lk(m);
-                cv.wait(lk, [this] { return stop || !jobs.empty(); });
+                // lane 0 takes whatever comes; the other lanes only help while lane 0 is busy (a context that sees one
+                // job at a time never creates a second device context)
+                cv.wait(lk, [&] { return (!jobs.empty() && (lane == 0 || lane0_busy)) || (stop && jobs.empty()); });
                 if (jobs.empty()) return;                            // stop requested and nothing left
                 j = std::move(jobs.front());
                 jobs.pop_front();
+                if (lane == 0) lane0_busy = true;
             }
-            j();
+            if (!dev[lane] && tsqb_create(&dev[lane], dev[0]->device) != 0) dev[lane] = nullptr;
+            std::vector<double> held;                                // progress reported while an older job was unfinished
+            ProgressFn progress = [&](uint64_t done, uint64_t nb) {
+                if (!j.progress_cb) return;
+                const double v = nb ? (double)done / (double)nb : 1.0;
+                std::lock_guard<std::mutex> lk(dm);
+                if (head_seq != j.seq) { held.push_back(v); return; }
+                for (double h : held) j.progress_cb(j.id, h);
+                held.clear();
+                j.progress_cb(j.id, v);
+            };
+            const bool ok = dev[lane] != nullptr && j.run(dev[lane], &progress);
+            {
+                std::unique_lock<std::mutex> lk(dm);
+                dcv.wait(lk, [&] { return head_seq == j.seq; });
+                if (j.progress_cb) for (double h : held) j.progress_cb(j.id, h);
+                if (j.completion_cb) j.completion_cb(j.id, ok);     // may submit jobs to other contexts (test/test.cpp:247-262)
+                head_seq++;
+            }
+            dcv.notify_all();
+            if (lane == 0) { std::lock_guard<std::mutex> lk(m); lane0_busy = false; }
+            cv.notify_all();
         }
     }
 };
+
+// [p, p + n) are the bytes BEHIND a caller's buffer.  The reference's memory path encodes in place, so its last block
+// simply reads them (tsq_threads.cpp:109; <= 19 bytes, 72 with extensions) and they shape the last block's stream.  Same
+// here -- unless a page of that range is not mapped at all, where the reference would have faulted: then zeros.
+static bool tail_is_mapped(const uint8_t* p, size_t n)
+{
+    const uintptr_t ps = (uintptr_t)sysconf(_SC_PAGESIZE);
+    const uintptr_t own = ((uintptr_t)p - 1) & ~(ps - 1);           // page of the buffer's last byte: mapped by definition
+    for (uintptr_t page = (uintptr_t)p & ~(ps - 1); page <= (((uintptr_t)p + n - 1) & ~(ps - 1)); page += ps) {
+        unsigned char vec;
+        if (page != own && mincore((void*)page, ps, &vec) != 0) return false;
+    }
+    return true;
+}
 }  // namespace
 
-struct TSQCompressionContext_MT   { tsqb_context* dev; bool verbose; JobThread* jobs; };
-struct TSQDecompressionContext_MT { tsqb_context* dev; bool verbose; JobThread* jobs; };
+struct TSQCompressionContext_MT   { tsqb_context* dev; bool verbose; JobEngine* jobs; };
+struct TSQDecompressionContext_MT { tsqb_context* dev; bool verbose; JobEngine* jobs; };
 
 extern "C" struct TSQCompressionContext_MT* tsqAllocateContextCompression_MT(bool verbose)
 {
     tsqb_context* d = nullptr;
     if (tsqb_create(&d, 0) != 0) { if (verbose) printf("Error: %s\n", tsqb_last_error()); return nullptr; }
-    return new TSQCompressionContext_MT{d, verbose, new JobThread()};
+    return new TSQCompressionContext_MT{d, verbose, new JobEngine(d)};
 }
 
 extern "C" void tsqDeallocateContextCompression_MT(struct TSQCompressionContext_MT* ctx)
@@ -865,7 +1063,7 @@ extern "C" struct TSQDecompressionContext_MT* tsqAllocateContextDecompression_MT
 {
     tsqb_context* d = nullptr;
     if (tsqb_create(&d, 0) != 0) { if (verbose) printf("Error: %s\n", tsqb_last_error()); return nullptr; }
-    return new TSQDecompressionContext_MT{d, verbose, new JobThread()};
+    return new TSQDecompressionContext_MT{d, verbose, new JobEngine(d)};
 }
 
 extern "C" void tsqDeallocateContextDecompression_MT(struct TSQDecompressionContext_MT* ctx)
@@ -899,35 +1097,37 @@ static bool store_output(uint8_t* blob, uint64_t n, uint8_t** out, size_t* szout
     return ok;
 }
 
-extern "C" bool tsqCompress_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
-                               bool outfile, bool useextensions, uint32_t level)
+// one compression job on device context `dev` (tsq_threads.cpp:278-410 + the pipeline behind it)
+static bool compress_job(tsqb_context* dev, bool verbose, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout, bool outfile,
+                         bool useextensions, const ProgressFn* prog)
 {
-    (void)level;
-    if (!ctx || !in || szin == 0 || !out || szout == 0) return false;          // tsq_threads.cpp:415-418
     std::vector<uint8_t> store;
     const uint8_t* p; size_t n;
-    if (!load_input(in, szin, infile, store, &p, &n, ctx->verbose)) return false;
+    if (!load_input(in, szin, infile, store, &p, &n, verbose)) return false;
+    // memory input: the last block sees the caller's bytes behind the buffer, as in the reference (tsq_threads.cpp:109)
+    const uint32_t tail_n = useextensions ? 72u : 19u;
+    const uint8_t* tail = (!infile && n && tail_is_mapped(p + n, tail_n)) ? p + n : nullptr;
     uint8_t* blob = nullptr; uint64_t bn = 0;
-    if (tsqb_compress_buffer(ctx->dev, p, n, g_container_block.load(), useextensions ? 1u : 0u, &blob, &bn) != 0) {
-        if (ctx->verbose) printf("Error: %s\n", tsqb_last_error());
+    if (compress_any(dev, p, n, tail, tail ? tail_n : 0u, g_container_block.load(), useextensions ? 1u : 0u, nullptr, 0, &blob, &bn, prog) != 0) {
+        if (verbose) printf("Error: %s\n", tsqb_last_error());
         return false;
     }
-    return store_output(blob, bn, out, szout, outfile, ctx->verbose);
+    return store_output(blob, bn, out, szout, outfile, verbose);
 }
 
-extern "C" bool tsqDecompress_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
-                                 bool outfile)
+static bool decompress_job(tsqb_context* dev, bool verbose, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout, bool outfile,
+                           const ProgressFn* prog)
 {
-    if (!ctx || !in || szin == 0 || !out || szout == 0) return false;          // tsq_threads.cpp:864-867
     std::vector<uint8_t> store;
     const uint8_t* p; size_t n;
-    if (!load_input(in, szin, infile, store, &p, &n, ctx->verbose)) return false;
+    if (!load_input(in, szin, infile, store, &p, &n, verbose)) return false;
+    if (n < 16 || memcmp(p, "TSQ1", 4) != 0) { if (verbose) printf("Error: not a TSQ1 container.\n"); return false; }   // tsq_threads.cpp:728-730
     uint8_t* blob = nullptr; uint64_t bn = 0;
-    if (tsqb_decompress_buffer(ctx->dev, p, n, &blob, &bn) != 0) {
-        if (ctx->verbose) printf("Error: %s\n", tsqb_last_error());
+    if (decompress_any(dev, p, n, nullptr, 0, &blob, &bn, prog) != 0) {
+        if (verbose) printf("Error: %s\n", tsqb_last_error());
         return false;
     }
-    return store_output(blob, bn, out, szout, outfile, ctx->verbose);
+    return store_output(blob, bn, out, szout, outfile, verbose);
 }
 
 // ---- asynchronous job API (tsq_threads.cpp:278-410, :679-859)
@@ -935,16 +1135,20 @@ extern "C" uint32_t tsqCompressAsync_MT(struct TSQCompressionContext_MT* ctx, ui
                                         size_t* szout, bool outfile, bool useextensions, uint32_t level,
                                         std::function<void(uint32_t, bool)> completion_cb, std::function<void(uint32_t, double)> progress_cb)
 {
+    (void)level;                                                     // stored and never read by the reference (tsq_threads.cpp:98,112)
     if (!ctx || !in || (!infile && szin == 0) || !out || !szout) {    // early failure: completion(0, false), id 0 (:296-306)
         if (completion_cb) completion_cb(0, false);
         return 0;
     }
-    return ctx->jobs->submit([=](uint32_t id) {
-        const bool ok = tsqCompress_MT(ctx, in, szin ? szin : 1, infile, out, szout, outfile, useextensions, level);
-        if (ctx->verbose) printf("Compression job %u %s\n", id, ok ? "done" : "failed");
-        if (ok && progress_cb) progress_cb(id, 1.0);
+    JobEngine::Job j;
+    const bool verbose = ctx->verbose;
+    j.run = [=](tsqb_context* dev, const ProgressFn* prog) { return compress_job(dev, verbose, in, szin, infile, out, szout, outfile, useextensions, prog); };
+    j.completion_cb = [=](uint32_t id, bool ok) {
+        if (verbose) printf("Compression job %u %s\n", id, ok ? "done" : "failed");
         if (completion_cb) completion_cb(id, ok);
-    });
+    };
+    j.progress_cb = progress_cb;
+    return ctx->jobs->submit(std::move(j));
 }
 
 extern "C" uint32_t tsqDecompressAsync_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out,
@@ -955,10 +1159,41 @@ extern "C" uint32_t tsqDecompressAsync_MT(struct TSQDecompressionContext_MT* ctx
         if (completion_cb) completion_cb(0, false);
         return 0;
     }
-    return ctx->jobs->submit([=](uint32_t id) {
-        const bool ok = tsqDecompress_MT(ctx, in, szin ? szin : 1, infile, out, szout, outfile);
-        if (ctx->verbose) printf("Decompression job %u %s\n", id, ok ? "done" : "failed");
-        if (ok && progress_cb) progress_cb(id, 1.0);
+    JobEngine::Job j;
+    const bool verbose = ctx->verbose;
+    j.run = [=](tsqb_context* dev, const ProgressFn* prog) { return decompress_job(dev, verbose, in, szin, infile, out, szout, outfile, prog); };
+    j.completion_cb = [=](uint32_t id, bool ok) {
+        if (verbose) printf("Decompression job %u %s\n", id, ok ? "done" : "failed");
         if (completion_cb) completion_cb(id, ok);
-    });
+    };
+    j.progress_cb = progress_cb;
+    return ctx->jobs->submit(std::move(j));
+}
+
+// ---- synchronous buffer API: submit, then wait for the completion callback -- exactly what the reference does
+// (tsq_threads.cpp:413-441, :862-890)
+namespace {
+struct Waiter {
+    std::mutex m; std::condition_variable cv; bool done = false, ok = false;
+    void set(bool v) { { std::lock_guard<std::mutex> lk(m); done = true; ok = v; } cv.notify_all(); }
+    bool wait() { std::unique_lock<std::mutex> lk(m); cv.wait(lk, [&] { return done; }); return ok; }
+};
+}  // namespace
+
+extern "C" bool tsqCompress_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
+                               bool outfile, bool useextensions, uint32_t level)
+{
+    if (!ctx || !in || szin == 0 || !out || szout == 0) return false;          // tsq_threads.cpp:415-418
+    Waiter w;
+    tsqCompressAsync_MT(ctx, in, szin, infile, out, szout, outfile, useextensions, level, [&w](uint32_t, bool ok) { w.set(ok); }, nullptr);
+    return w.wait();
+}
+
+extern "C" bool tsqDecompress_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,
+                                 bool outfile)
+{
+    if (!ctx || !in || szin == 0 || !out || szout == 0) return false;          // tsq_threads.cpp:864-867
+    Waiter w;
+    tsqDecompressAsync_MT(ctx, in, szin, infile, out, szout, outfile, [&w](uint32_t, bool ok) { w.set(ok); }, nullptr);
+    return w.wait();
 }

@@ -1,4 +1,4 @@
-// tsq_container.cu -- TSQ1 framing on the device and the encode dispatcher.
+// tsq_container.cu -- TSQ1 framing on the device and the encode / decode dispatchers.
 //
 // Container (reference turbosqueeze.cpp:64-67,78-84; tsq_threads.cpp:333-335,218-240):
 //   "TSQ1" | n_blocks u32 | total_uncompressed u64 | n_blocks x { u24 (size | 0x800000 if ext), stream }
@@ -7,8 +7,13 @@
 namespace tsqb {
 
 cudaError_t launch_encode_scalar(const EncodeArgs& a, bool ext, cudaStream_t st);
-cudaError_t launch_encode_warp(const EncodeArgs& a, cudaStream_t st);
 cudaError_t launch_encode_batch(const EncodeArgs& a, bool ext, cudaStream_t st);
+cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair, int slot_cap);
+#ifdef TSQB_XCHECK   // round-1 v1 kernels, kept as cross-checks in the test-only library (csrc/xcheck/)
+cudaError_t launch_encode_warp(const EncodeArgs& a, cudaStream_t st);
+cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
+cudaError_t launch_decode_subwarp(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st);
+#endif
 
 uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override)
 {
@@ -29,8 +34,30 @@ bool encode_wants_fat(int impl, uint32_t n_slots) { return impl == 3 && n_slots 
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int /*sm_count*/, cudaStream_t st)
 {
     if (impl == 1) return launch_encode_scalar(a, ext, st);
+#ifdef TSQB_XCHECK
     if (impl == 2) return ext ? cudaErrorInvalidValue : launch_encode_warp(a, st);
+#else
+    if (impl == 2) return cudaErrorInvalidValue;                     // the v1 warp kernel lives in the cross-check library only
+#endif
     return launch_encode_batch(a, ext, st);
+}
+
+// lanes: 0 = auto (35 for the no-extension format, 34 for the extension format);
+// 34 = walker + copier kernel (tsq_decode_split.cu), lane per symbol, both formats;
+// 35 = the same kernel choosing per block between the lane-per-pair copier (64 symbols per step) and, for (nearly)
+//      incompressible blocks, the lane-per-symbol one; no-extension format (the extension format runs as 34).
+// Cross-check library only: 1..32 = sub-warp pair-step kernel with that many lanes per block, 33 = v1 warp-per-block
+// step kernel (no-extension format).
+cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st, int slot_cap)
+{
+    if (lanes <= 0) lanes = ext ? 34 : 35;
+    if (lanes == 34 || lanes == 35) return launch_decode_split(a, ext, sm_count, st, lanes == 35, slot_cap);
+#ifdef TSQB_XCHECK
+    if (lanes == 33) return ext ? cudaErrorInvalidValue : launch_decode_warp(a, sm_count, st);
+    return launch_decode_subwarp(a, lanes, ext, sm_count, st);
+#else
+    return cudaErrorInvalidValue;
+#endif
 }
 
 // ---- pack: offsets = exclusive scan of (3 + size), one CTA (n_blocks is at most a few million)
@@ -112,7 +139,7 @@ __global__ void index_kernel(const uint8_t* __restrict__ c, uint64_t csize, uint
         const uint32_t v = (uint32_t)c[at] | ((uint32_t)c[at + 1] << 8) | ((uint32_t)c[at + 2] << 16);
         const uint32_t len = v & 0x7FFFFFu;
         at += 3;
-        if (len == 0 || at + len > csize) break;                     // turbosqueeze.cpp:136
+        if (len < 3 || at + len > csize) break;                      // turbosqueeze.cpp:136; a block is at least its u24 size header
         offs[n] = at; sizes[n] = len; ext[n] = v >> 23;
         n++;
         at += len;

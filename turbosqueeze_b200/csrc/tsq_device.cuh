@@ -39,8 +39,8 @@ struct DecodeArgs {
     uint32_t*       osizes;
 };
 
-// encode_impl: 1 = scalar (one thread per block), 2 = warp per block (byte-at-a-time emitter),
-// 3 = warp per block with token batches (tsq_encode_batch.cu, the default, both formats).
+// encode_impl: 1 = scalar (one thread per block), 3 = warp per block with token batches (tsq_encode_batch.cu, the default,
+// both formats); 2 = round-1 v1 warp kernel, cross-check library only (-DTSQB_XCHECK).
 cudaError_t launch_encode(const EncodeArgs& a, int impl, bool ext, int sm_count, cudaStream_t st);
 // bytes of one hash table of launch_encode(impl)
 uint32_t    encode_table_bytes(int impl, bool fat);
@@ -49,9 +49,8 @@ bool        encode_wants_fat(int impl, uint32_t n_slots);
 // how many hash tables launch_encode(impl) will use for nb blocks (caller sizes a.tables from it)
 uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);
 
-// lanes: lanes cooperating on one block (1..32, power of two)
+// lanes: see tsq_container.cu (34 / 35 = walker + copier kernel; 1..33 only in the cross-check library)
 cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st, int slot_cap = 0);
-int         decode_lanes_auto(uint64_t nb, int sm_count);
 
 cudaError_t launch_pack(const uint8_t* slots, uint64_t stride, const uint32_t* sizes, uint64_t nb,
                         uint64_t total_u, uint32_t ext, uint8_t* container, uint64_t* total_out,

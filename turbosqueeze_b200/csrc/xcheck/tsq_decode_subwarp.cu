@@ -1,5 +1,6 @@
-// tsq_decode.cu -- the sub-warp pair-step decoder (round-1 v1, kept as a cross-check; the production decoder is
-// tsq_decode_split.cu) and the decode dispatcher.
+// tsq_decode_subwarp.cu -- the sub-warp pair-step decoder (round-1 v1).  CROSS-CHECK ONLY: built into the test-only
+// library tests/xcheck/libturbosqueeze_b200_xcheck.so (-DTSQB_XCHECK), not into the product; the production decoder is
+// tsq_decode_split.cu.
 //
 // Semantics: reference tsqDecodeNoext (tsq_decode.cpp:42-126) and the extension variant
 // (tsq_decode.cpp:137-314), restated around a "pair step": the reference's inner body handles one
@@ -16,7 +17,7 @@
 // Unlike the reference, which copies a blind 16 bytes per symbol and over-writes up to ~100 bytes
 // past the block (tsq_decode.cpp:60-123), every store is clipped at the block's decoded size so
 // that blocks can be packed back to back in HBM.
-#include "tsq_device.cuh"
+#include "../tsq_device.cuh"
 
 namespace tsqb {
 
@@ -117,15 +118,6 @@ __global__ void __launch_bounds__(128) decode_kernel(DecodeArgs a)
     }
 }
 
-int decode_lanes_auto(uint64_t nb, int sm_count)
-{
-    // fill >= 16 warps per SM when the block count allows it; never wider than a warp
-    const uint64_t want_warps = (uint64_t)sm_count * 16u;
-    int lanes = 32;
-    while (lanes > 1 && nb * (uint64_t)lanes / 32u > want_warps * 2u) lanes >>= 1;
-    return lanes;
-}
-
 template <int W, bool EXT>
 static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream_t st)
 {
@@ -139,20 +131,9 @@ static cudaError_t launch_decode_t(const DecodeArgs& a, int sm_count, cudaStream
     return cudaGetLastError();
 }
 
-cudaError_t launch_decode_warp(const DecodeArgs& a, int sm_count, cudaStream_t st);
-cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair, int slot_cap);
-
-// lanes: 0 = auto (35 for the no-extension format, 34 for the extension format);
-// 34 = walker + copier kernel (tsq_decode_split.cu), lane per symbol, both formats;
-// 35 = the same kernel choosing per block between the lane-per-pair copier (64 symbols per step) and, for (nearly)
-//      incompressible blocks, the lane-per-symbol one; no-extension format (the extension format runs as 34);
-// 1..32 = sub-warp kernel with that many lanes per block; 33 = force the warp-per-block
-// step kernel (tsq_decode_warp.cu), 32 = force the pair-step kernel at full warp width
-cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st, int slot_cap)
+// lanes = 1, 2, 4, 8, 16, 32 lanes per block
+cudaError_t launch_decode_subwarp(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st)
 {
-    if (lanes <= 0) lanes = ext ? 34 : 35;
-    if (lanes == 34 || lanes == 35) return launch_decode_split(a, ext, sm_count, st, lanes == 35, slot_cap);
-    if (lanes == 33) return ext ? cudaErrorInvalidValue : launch_decode_warp(a, sm_count, st);
 #define TSQB_CASE(Wv) case Wv: return ext ? launch_decode_t<Wv, true>(a, sm_count, st) : launch_decode_t<Wv, false>(a, sm_count, st);
     switch (lanes) {
         TSQB_CASE(1) TSQB_CASE(2) TSQB_CASE(4) TSQB_CASE(8) TSQB_CASE(16) TSQB_CASE(32)

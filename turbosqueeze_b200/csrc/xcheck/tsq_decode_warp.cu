@@ -1,4 +1,4 @@
-// tsq_decode_warp.cu -- one WARP per block, 32 symbols per step, stream staged in shared memory.
+// tsq_decode_warp.cu (CROSS-CHECK ONLY: test library tests/xcheck/libturbosqueeze_b200_xcheck.so, not the product) -- one WARP per block, 32 symbols per step, stream staged in shared memory.
 //
 // Semantics: reference tsqDecodeNoext (tsq_decode.cpp:42-126), bit-exact on [0, size).
 //
@@ -15,7 +15,7 @@
 // of the pairs before them: they run in follow-up rounds, each round releasing every symbol whose
 // source ends before the first still-pending pair (sources always precede their own pair,
 // tsq_encode.cpp:139-141, so every round makes progress).
-#include "tsq_device.cuh"
+#include "../tsq_device.cuh"
 
 namespace tsqb {
 

@@ -1,4 +1,4 @@
-// tsq_encode_warp.cu -- one WARP per block: the greedy parse with 32 positions probed at a time.
+// tsq_encode_warp.cu (CROSS-CHECK ONLY: test library tests/xcheck/libturbosqueeze_b200_xcheck.so, not the product) -- one WARP per block: the greedy parse with 32 positions probed at a time.
 //
 // Reference semantics: tsqEncodeNoext (tsq_encode.cpp:48-189); bit-exact, see SURVEY.md 8(a).
 //
@@ -22,7 +22,7 @@
 // length k from lane H the next probe is lane H+k of the same window (lanes in between are not in P).
 // Match length is a 16-lane byte compare + ballot.  The token stream writer keeps the open control
 // and size bytes in (warp-uniform) registers.
-#include "tsq_encode_common.cuh"
+#include "../tsq_encode_common.cuh"
 
 namespace tsqb {
 

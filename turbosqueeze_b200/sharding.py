@@ -38,48 +38,89 @@ def container_header(n_blocks, total_uncompressed):
     return b"TSQ1" + struct.pack("<IQ", n_blocks, total_uncompressed)
 
 
-def gather_bodies(body, dst=0, group=None):
+def gather_bodies(body, dst=0, group=None, length=None, out=None, out_offset=0):
     """Variable-length gather of one uint8 tensor per rank to `dst`, in rank order.
 
-    body: 1-D uint8 tensor (this rank's container body: u24 length prefixes + block streams).
-    Returns (concatenated tensor on dst | None elsewhere, list of per-rank byte counts).
+    body:   1-D uint8 tensor; this rank's bytes are body[:length] (length: 1-element int64 tensor on the same device,
+            e.g. straight from tsqb_pack_container, or None = all of body).  Passing the device-side length avoids a
+            host synchronisation per rank: the byte counts are all-gathered as they are and read back ONCE.
+    out:    optional destination buffer on dst (the bytes land at out[out_offset:]); allocated when None.
+    Returns (destination tensor holding all bodies back to back from out_offset | None off dst, list of byte counts).
     """
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     dev = body.device
-    n = torch.tensor([body.numel()], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    if length is None:
+        n = torch.tensor([body.numel()], dtype=torch.int64, device=dev)
+    else:
+        n = length.reshape(1).to(torch.int64)
+    counts_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, n, group=group)
+    counts = [int(c) for c in counts_t.cpu().tolist()]                # the one host synchronisation of the gather
+    mine = counts[rank]
     if rank == dst:
-        out = torch.empty(sum(counts), dtype=torch.uint8, device=dev)
-        at, ops = 0, []
+        if out is None:
+            out = torch.empty(out_offset + sum(counts), dtype=torch.uint8, device=dev)
+        at, ops = out_offset, []
         for r, c in enumerate(counts):
             if r == dst:
-                out[at:at + c].copy_(body)
+                out[at:at + c].copy_(body[:c])
             elif c:
                 ops.append(dist.P2POp(dist.irecv, out[at:at + c], r, group))
             at += c
-        for w in (dist.batch_isend_irecv(ops) if ops else []):
+        for w in (dist.batch_isend_irecv(ops) if ops else []):       # one grouped NCCL launch straight into `out`
             w.wait()
         return out, counts
-    if body.numel():
-        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, body.contiguous(), dst, group)]):
+    if mine:
+        for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, body[:mine], dst, group)]):
             w.wait()
     return None, counts
 
 
-def gather_container(local_container, total_uncompressed, n_blocks_total, dst=0, group=None):
+def gather_container(local_container, total_uncompressed, n_blocks_total, dst=0, group=None, length=None):
     """Assemble one TSQ1 container on `dst` from per-rank containers (each rank's own header is dropped).
 
-    local_container: uint8 tensor holding a TSQ1 container of this rank's blocks (what
-    Context.pack_container / tsqb_pack_container produce).  Returns the uint8 tensor on dst, else None.
+    local_container: uint8 tensor holding a TSQ1 container of this rank's blocks (what Context.pack_container /
+    tsqb_pack_container produce); `length`: its device-side length tensor (None = the whole tensor).
+    The header is written in place in front of the gathered bodies -- no second copy of the container.
+    Returns the uint8 tensor on dst, else None.
     """
-    body, _ = gather_bodies(local_container[HEADER:], dst=dst, group=group)
-    if body is None:
+    body_len = None if length is None else length.reshape(1).to(torch.int64) - HEADER
+    out, _ = gather_bodies(local_container[HEADER:], dst=dst, group=group, length=body_len, out_offset=HEADER)
+    if out is None:
         return None
-    hdr = torch.frombuffer(bytearray(container_header(n_blocks_total, total_uncompressed)), dtype=torch.uint8).to(body.device)
-    return torch.cat([hdr, body])
+    hdr = torch.frombuffer(bytearray(container_header(n_blocks_total, total_uncompressed)), dtype=torch.uint8)
+    out[:HEADER].copy_(hdr, non_blocking=True)
+    return out
+
+
+def encode_sharded(ctx, host_buf, total, block, ext=0, dst=0, group=None):
+    """The N-GPU encode path: ONE input stream of `total` bytes, rank r encodes the contiguous block
+    range byte_range() gives it -- its shard plus INPUT_PAD bytes of the following shard, because the last block of a
+    shard reads a few bytes past itself (tsq_encode.cpp:74,126-128; zeros behind the very end) -- frames its streams
+    as a TSQ1 body on its own GPU (tsqb_pack_container) and the bodies are gathered to `dst` over NCCL.
+
+    ctx: turbosqueeze_b200.Context on this rank's device; host_buf: numpy uint8 array holding the whole stream (every
+    rank reads only its own range).  Returns (container tensor on dst | None, dict of timings-free bookkeeping).
+    """
+    import numpy as np
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi, hi_tail = byte_range(total, block, rank, world)
+    n = hi - lo
+    dev = torch.device("cuda", ctx.device)
+    d_in = torch.zeros(n + INPUT_PAD, dtype=torch.uint8, device=dev)
+    if hi_tail > lo:
+        d_in[: hi_tail - lo].copy_(torch.from_numpy(np.ascontiguousarray(host_buf[lo:hi_tail])))
+    nb_total = (total + block - 1) // block
+    if n:
+        slots, sizes = ctx.encode_blocks(d_in, n, block, ext)
+        cont, clen = ctx.pack_container(slots, sizes, block, n, ext)
+    else:                                                             # more ranks than blocks: an empty body
+        cont = torch.zeros(HEADER, dtype=torch.uint8, device=dev)
+        clen = torch.tensor([HEADER], dtype=torch.int64, device=dev)
+    out = gather_container(cont, total, nb_total, dst=dst, group=group, length=clen)
+    return out, {"lo": lo, "hi": hi, "hi_tail": hi_tail, "blocks": (n + block - 1) // block}
 
 
 def all_gather_decoded(local_out, group=None):
@@ -88,12 +129,14 @@ def all_gather_decoded(local_out, group=None):
     world = dist.get_world_size(group)
     dev = local_out.device
     n = torch.tensor([local_out.numel()], dtype=torch.int64, device=dev)
-    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
-    dist.all_gather(counts, n, group=group)
-    counts = [int(c.item()) for c in counts]
+    counts_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, n, group=group)
+    counts = [int(c) for c in counts_t.cpu().tolist()]
     cap = max(counts) if counts else 0
     padded = torch.zeros(cap, dtype=torch.uint8, device=dev)
     padded[: local_out.numel()].copy_(local_out)
-    parts = [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(world)]
-    dist.all_gather(parts, padded, group=group)
-    return torch.cat([p[:c] for p, c in zip(parts, counts)])
+    parts = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(parts, padded, group=group)
+    if all(c == cap for c in counts):
+        return parts
+    return torch.cat([parts[r * cap: r * cap + c] for r, c in enumerate(counts)])
