@@ -25,6 +25,8 @@ def main():
         ctx.set_option("encode_hints", int(os.environ["ENC_HINTS"]))
     if os.environ.get("DEC_SLOTS"):
         ctx.set_option("decode_slots", int(os.environ["DEC_SLOTS"]))
+    if os.environ.get("ENC_FAT"):
+        ctx.set_option("encode_fat", int(os.environ["ENC_FAT"]))
     if os.environ.get("L2_FETCH"):
         ctx.set_option("l2_fetch", int(os.environ["L2_FETCH"]))
     buf = W.fill(kind, n, seed=20240917)

@@ -47,6 +47,22 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_QUEUE
 #define TSQB_DEC_QUEUE 128
 #endif
+// round-2 development knobs (scripts/build_variants.sh; profiles/r02_experiments.md records what they measured)
+#ifndef TSQB_DEC_FARNP
+#define TSQB_DEC_FARNP 0           // lane-per-pair copier: far-match source words loaded without per-word predicates (2.73 -> 4.45 ms:
+#endif                             // the far loads are bound by L1TEX wavefronts -- every scattered lane is its own 128-byte line)
+#ifndef TSQB_DEC_FARWIDE
+#define TSQB_DEC_FARWIDE 1         // far-match source = one aligned 128-bit load (a second one only when the bytes cross its end)
+#endif                             // instead of up to five 32-bit loads: ~2.6 -> ~1.3 L1TEX wavefronts per far symbol
+#ifndef TSQB_DEC_PEND2
+#define TSQB_DEC_PEND2 1           // lane-per-pair copier: in-order copies take both symbols of a pair at once (half-warp each), one packed shuffle per symbol
+#endif
+#ifndef TSQB_DEC_FLUSH2
+#define TSQB_DEC_FLUSH2 1          // lane-per-pair copier: flush of a step = two predicated 128-bit moves (a step leaves <= 65 units)
+#endif
+#ifndef TSQB_DEC_WMASK
+#define TSQB_DEC_WMASK 1           // walker: the 4-group path masks its ring addresses instead of requiring that it does not wrap
+#endif
 constexpr uint32_t kQueue    = TSQB_DEC_QUEUE;       // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
 constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
@@ -226,10 +242,18 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                 // every limit -- and of the end of the stream ring, so that the walk can use a plain shared-memory pointer: the
                 // per-group tests and the ring wrap (mask + base) drop out of the serial chain (load, 3 ALU, load).
                 if ((k & 3u) == 0 && p + 4u * 133u + 4u * kLook <= p_safe && (k - cons) + 16u <= kQueue && j + 4u * 128u + (EXT ? 512u : 128u) < size && !EXT &&
-                    (p & kInMask) + 4u * 133u + 8u <= kInRing) {
+                    (TSQB_DEC_WMASK || (p & kInMask) + 4u * 133u + 8u <= kInRing)) {
+#if TSQB_DEC_WMASK
+                    // ring addresses are masked (one LOP3 on the chain) so that a lane near the end of its ring stays on
+                    // this path: lanes of one warp that sit on different paths execute them one after the other
+                    uint32_t pr = p;
+                    const uint32_t dlt = 0;
+                    auto lds_u8 = [&](uint32_t pos) -> uint32_t { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(rbase + (pos & kInMask))); return v; };
+#else
                     uint32_t pr = rbase + (p & kInMask);          // shared address of stream position p
                     const uint32_t dlt = p - pr;                  // stream position = shared address + dlt
                     auto lds_u8 = [](uint32_t ad) -> uint32_t { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ad)); return v; };
+#endif
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         const uint32_t dsl = dbase + ((k & kQMask) << 3);
@@ -338,6 +362,38 @@ __device__ __forceinline__ void load16_smem(uint32_t base, uint32_t mask, uint32
     }
 #pragma unroll
     for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
+}
+
+// The (up to) 16 bytes of a far match source -- bytes of this block that an earlier step flushed to HBM -- as the five
+// 32-bit words around them (the caller funnel-shifts by the address's low two bits, as for the narrow loads).
+// One aligned 128-bit load covers the source unless it crosses the next 16-byte boundary (then a second one): a scattered
+// warp-wide load costs one L1TEX wavefront per lane and instruction, so fewer, wider instructions are what counts.
+// Never touches a 16-byte unit the source does not reach.
+// far_issue only issues the loads; far_words turns them into w[] -- called where the bytes are needed, so that the DRAM / L2
+// latency of a step's far sources runs under its shared-memory loads.
+__device__ __forceinline__ void far_issue(const uint8_t* src, uint32_t len, uint4& A, uint4& B)
+{
+    const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
+    const uint4* g = reinterpret_cast<const uint4*>(ad & ~(uintptr_t)15);
+    A = __ldcg(g);
+    B = make_uint4(0, 0, 0, 0);
+    if ((uint32_t)(ad & 15u) + len > 16u) B = __ldcg(g + 1);
+}
+
+__device__ __forceinline__ void far_words(const uint8_t* src, const uint4& A, const uint4& B, uint32_t w[5])
+{
+    // words X[0..7] = A.x A.y A.z A.w B.x B.y B.z B.w; wanted: X[(o >> 2) + m], m = 0..4 -- two levels of selects
+    const uint32_t o = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 15u);
+    const bool s2 = (o & 8u) != 0, s1 = (o & 4u) != 0;
+    const uint32_t y0 = s2 ? A.z : A.x, y1 = s2 ? A.w : A.y, y2 = s2 ? B.x : A.z, y3 = s2 ? B.y : A.w, y4 = s2 ? B.z : B.x, y5 = s2 ? B.w : B.y;
+    w[0] = s1 ? y1 : y0; w[1] = s1 ? y2 : y1; w[2] = s1 ? y3 : y2; w[3] = s1 ? y4 : y3; w[4] = s1 ? y5 : y4;
+}
+
+__device__ __forceinline__ void far_load_wide(const uint8_t* src, uint32_t len, uint32_t w[5])
+{
+    uint4 A, B;
+    far_issue(src, len, A, B);
+    far_words(src, A, B, w);
 }
 
 // The bytes of one symbol into a ring: byte t is stored iff bit t of `lenmask` is set (ptxas materialises the mask
@@ -537,12 +593,16 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0,
                     if (sm_src) load16_smem(fbase, fmask, fpos, v, wrap);
                     if (far) {
                         const uintptr_t ad = reinterpret_cast<uintptr_t>(o_al + srcq);
-                        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
                         const uint32_t sh = (uint32_t)(ad & 3u) * 8u;
                         uint32_t w[5];
+#if TSQB_DEC_FARWIDE
+                        far_load_wide(o_al + srcq, len, w);
+#else
+                        const uint32_t* g32 = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
 #pragma unroll
                         for (int m = 0; m < 5; m++)                              // never touch a word past the source
                             w[m] = ((uint32_t)(ad & 3u) + len > 4u * m) ? __ldcg(g32 + m) : 0u;
+#endif
 #pragma unroll
                         for (int m = 0; m < 4; m++) v[m] = __funnelshift_r(w[m], w[m + 1], sh);
                     }
@@ -668,7 +728,20 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
         uint32_t F = oal;
 
         auto flush_units = [&](uint32_t E) {
-            for (uint32_t at = F + 16u * lane; at < E; at += 512u) {
+#if TSQB_DEC_FLUSH2
+            // a step leaves at most 65 complete units behind; a text step ~20: two predicated moves per lane, a third when full
+#pragma unroll
+            for (int rep = 0; rep < 2; rep++) {
+                const uint32_t at = F + 16u * lane + 512u * rep;
+                if (at < E) {
+                    uint4 x;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
+                    *reinterpret_cast<uint4*>(o_al + at) = x;
+                }
+            }
+            if (F + 1024u < E)
+#endif
+            for (uint32_t at = F + 16u * lane + (TSQB_DEC_FLUSH2 ? 1024u : 0u); at < E; at += 512u) {
                 uint4 x;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
                 *reinterpret_cast<uint4*>(o_al + at) = x;
@@ -693,8 +766,17 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
         auto far_load = [&](uint32_t srcq, uint32_t len, uint32_t w[5]) {
             const uintptr_t ad = reinterpret_cast<uintptr_t>(o_al + srcq);
             const uint32_t* g32 = reinterpret_cast<const uint32_t*>(ad & ~(uintptr_t)3);
+#if TSQB_DEC_FARNP
+            // A far source ends more than OUT_RING - 1040 >= 1008 bytes before this step's first output byte (srcq +
+            // OUT_RING < J1 + 16 and J1 <= J0 + 1024): all five words lie inside bytes of THIS block that earlier steps
+            // flushed, so they can be read without per-word predicates (only `len` of the 16 bytes are used)
+            (void)len;
+#pragma unroll
+            for (int m = 0; m < 5; m++) w[m] = __ldcg(g32 + m);
+#else
 #pragma unroll
             for (int m = 0; m < 5; m++) w[m] = ((uint32_t)(ad & 3u) + len > 4u * m) ? __ldcg(g32 + m) : 0u;
+#endif
         };
         // one pending symbol (source inside this step's output), lane-per-byte, after everything before it is in place
         auto copy_in_order = [&](uint32_t s_q, uint32_t s_src, uint32_t s_len) {
@@ -752,8 +834,14 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                 const bool pend0 = act0 && !now0, pend1 = act1 && !now1;
                 const bool far0 = now0 && !l0 && src0 + OUT_RING < J1 + 16u, far1 = now1 && !l1 && src1 + OUT_RING < J1 + 16u;
                 uint32_t w0[5], w1[5];
+#if TSQB_DEC_FARWIDE
+                uint4 fa0, fb0, fa1, fb1;
+                if (far0) far_issue(o_al + src0, len0, fa0, fb0);                // both symbols' far loads fly together,
+                if (far1) far_issue(o_al + src1, len1, fa1, fb1);                // under the shared-memory loads below
+#else
                 if (far0) far_load(src0, len0, w0);                              // both symbols' far loads fly together
                 if (far1) far_load(src1, len1, w1);
+#endif
                 uint32_t v0[4] = {0, 0, 0, 0}, v1[4] = {0, 0, 0, 0};
                 {
                     const uint32_t fbase = l0 ? ibase : obase, fmask = l0 ? kInMask : kOMask, fpos = l0 ? sp0 : src0;
@@ -768,11 +856,17 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                     if (sm_src) load16_smem(fbase, fmask, fpos, v1, wrap);
                 }
                 if (far0) {
+#if TSQB_DEC_FARWIDE
+                    far_words(o_al + src0, fa0, fb0, w0);
+#endif
                     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(o_al + src0) & 3u) * 8u;
 #pragma unroll
                     for (int m = 0; m < 4; m++) v0[m] = __funnelshift_r(w0[m], w0[m + 1], sh);
                 }
                 if (far1) {
+#if TSQB_DEC_FARWIDE
+                    far_words(o_al + src1, fa1, fb1, w1);
+#endif
                     const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(o_al + src1) & 3u) * 8u;
 #pragma unroll
                     for (int m = 0; m < 4; m++) v1[m] = __funnelshift_r(w1[m], w1[m + 1], sh);
@@ -780,8 +874,32 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                 if (now0) store16(obase, kOMask, q0, v0, (q0 & kOMask) + 16u > OUT_RING, (1u << len0) - 1u);
                 if (now1) store16(obase, kOMask, q1, v1, (q1 & kOMask) + 16u > OUT_RING, (1u << len1) - 1u);
 
-                // ---- symbols whose source lies inside this step's output: in position order (pair by pair, first
-                // symbol before second); sources always precede their own pair (tsq_encode.cpp:139-141)
+                // ---- symbols whose source lies inside this step's output: in position order, pair by pair; sources always
+                // precede their own pair (tsq_encode.cpp:139-141), so the two symbols of a pair never depend on each other
+#if TSQB_DEC_PEND2
+                {
+                    // one packed word per symbol: q - J0 (10 bits) | src + 16 - J0 (11 bits: a pending source starts at most
+                    // 15 bytes before the step) | len - 1 (4 bits).  Lanes 0..15 copy the pair's first symbol byte per lane,
+                    // lanes 16..31 its second one, at the same time.
+                    const uint32_t pk0 = pend0 ? ((q0 - J0) | ((src0 + 16u - J0) << 10) | ((len0 - 1u) << 21)) : 0xFFFFFFFFu;
+                    const uint32_t pk1 = pend1 ? ((q1 - J0) | ((src1 + 16u - J0) << 10) | ((len1 - 1u) << 21)) : 0xFFFFFFFFu;
+                    uint32_t pm = __ballot_sync(FULL, pend0 || pend1);
+                    const uint32_t hl = lane & 15u, tb = J0 + hl;
+                    const bool second = lane >= 16u;
+                    while (pm) {
+                        const uint32_t pl = (uint32_t)__ffs((int)pm) - 1u;
+                        pm &= pm - 1u;
+                        const uint32_t a = __shfl_sync(FULL, pk0, pl), b = __shfl_sync(FULL, pk1, pl);
+                        const uint32_t pk = second ? b : a;
+                        __syncwarp();                                            // everything before this pair is in place
+                        if (pk != 0xFFFFFFFFu && hl <= (pk >> 21)) {
+                            uint32_t byte;
+                            asm volatile("ld.volatile.shared.u8 %0, [%1];" : "=r"(byte) : "r"(obase + ((tb + ((pk >> 10) & 0x7FFu) - 16u) & kOMask)) : "memory");
+                            asm volatile("st.volatile.shared.u8 [%0], %1;" ::"r"(obase + ((tb + (pk & 0x3FFu)) & kOMask)), "r"(byte) : "memory");
+                        }
+                    }
+                }
+#else
                 uint32_t pm0 = __ballot_sync(FULL, pend0), pm1 = __ballot_sync(FULL, pend1);
                 while (pm0 | pm1) {
                     const uint32_t pl = (uint32_t)__ffs((int)(pm0 | pm1)) - 1u;
@@ -791,6 +909,7 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                     copy_in_order(s_q, s_src, s_len);
                     if (first) pm0 &= ~(1u << pl); else pm1 &= ~(1u << pl);
                 }
+#endif
                 __syncwarp();
                 if (F & 15u) flush(J1, false); else if ((J1 & ~15u) > F) flush_units(J1 & ~15u);
                 kc += np;
