@@ -73,16 +73,19 @@ void tsqb_destroy(tsqb_context* ctx);
 uint64_t tsqb_slot_stride(uint32_t block_size);
 
 /* Knobs for benchmarking / tests.  Returns 0 when the key is known.
- *   "encode_impl"   0 = auto (token-batch kernel), 1 = scalar thread-per-block, 2 = round-1 v1 warp kernel (no-ext only),
- *                   3 = warp-per-block token batches (tsq_encode_batch.cu)
+ *   "encode_impl"   0 = auto (token-batch kernel), 1 = scalar thread-per-block, 3 = warp-per-block token batches
+ *                   (tsq_encode_batch.cu); 2 = round-1 v1 warp kernel: only in the test-only cross-check library
  *   "encode_slots"  0 = auto: hash tables (= blocks) in flight
  *   "encode_fat"    table format of the batch encoder: -1 = auto, 0 = 2^17 x u16, 1 = 32-byte sector entries
  *   "decode_lanes"  0 = auto (35, or 34 for the extension format); 35 = walker + copier kernel (tsq_decode_split.cu) choosing
- *                   per block between the lane-per-pair and the lane-per-symbol copier, 34 = lane per symbol only,
- *                   33 = v1 warp kernel (no-ext only), 1,2,4,8,16,32 = sub-warp pair-step kernel with that many lanes per block
+ *                   per block between the lane-per-pair and the lane-per-symbol copier, 34 = lane per symbol only;
+ *                   1..33 = the superseded round-1 kernels: only in the test-only cross-check library
  *   "decode_slots"  0 = auto; 1..30 = at most this many block slots (copier warps) per CTA of the walker + copier kernel
  *   "pipeline"      1 = the host-buffer calls overlap PCIe copies with kernels in chunks, 0 = one-shot staging
- *   "pipeline_min"  bytes below which the host-buffer calls stage in one shot */
+ *   "pipeline_min"  bytes below which the host-buffer calls stage in one shot
+ *   "pipe_chunks"   chunks a host buffer is cut into (1..16, default 6); "pipe_taper" 1 = chunks shrink towards the end
+ *   "stream_in"     1 (default) = compression streams every block's input in pieces while its encoder already runs
+ *                   (blocks >= 64 KiB), 0 = whole chunks; "stream_stagger" = transfers between the chunks' kernel starts */
 int tsqb_set_option(tsqb_context* ctx, const char* key, int64_t value);
 
 /*
@@ -213,11 +216,15 @@ bool tsqDecompress_MT(struct TSQDecompressionContext_MT* ctx, uint8_t* in, size_
 }
 
 /* turbosqueeze.h:543-544,615-616 -- the asynchronous job API.  As in the reference these two have C linkage but
- * C++ parameter types.  Jobs of one context run in submission order on the context's job thread (the reference's
- * writer thread, tsq_threads.cpp:192-275, is where its callbacks run too): progress_cb(id, 1.0) then
- * completion_cb(id, success).  Returns the job id (>= 1); on an early failure completion_cb(0, false) is invoked
- * and 0 returned (tsq_threads.cpp:296-306).  Callbacks may submit jobs to another context (test/test.cpp:247-262).
- * tsqDeallocateContext*_MT waits for the jobs in flight (tsq_context.cpp:150-155). */
+ * C++ parameter types.  Up to two jobs of one context run at the same time on the GPU (two job threads, each with device
+ * scratch of its own); their callbacks are delivered strictly in submission order, as from the reference's single writer
+ * thread (tsq_threads.cpp:192-275): progress_cb(id, blocks_done / n_blocks) once per block (:248-254, :654-655), then
+ * completion_cb(id, success) (:256-268).  Returns the job id (>= 1); on an early failure completion_cb(0, false) is
+ * invoked and 0 returned (tsq_threads.cpp:296-306).  Callbacks may submit jobs to another context
+ * (test/test.cpp:247-262).  tsqDeallocateContext*_MT waits for the jobs in flight (tsq_context.cpp:150-155).
+ * The synchronous calls above are "submit, then wait for the completion callback", as in the reference (:413-441).
+ * Memory input: the last block reads the caller's bytes behind the buffer (<= 19, 72 with extensions) exactly as the
+ * reference's in-place encoder does (tsq_threads.cpp:109); pages that are not mapped count as zeros. */
 #include <functional>
 extern "C" {
 uint32_t tsqCompressAsync_MT(struct TSQCompressionContext_MT* ctx, uint8_t* in, size_t szin, bool infile, uint8_t** out, size_t* szout,

@@ -9,6 +9,8 @@ buf = W.fill("text", n, seed=20240917)
 ctx = T.Context(0)
 if len(sys.argv) > 1: ctx.set_option("pipe_chunks", int(sys.argv[1]))
 if len(sys.argv) > 2: ctx.set_option("pipe_taper", int(sys.argv[2]))
+if len(sys.argv) > 3: ctx.set_option("stream_in", int(sys.argv[3]))
+if len(sys.argv) > 4: ctx.set_option("stream_stagger", int(sys.argv[4]))
 pin = torch.empty(n + 128, dtype=torch.uint8, pin_memory=True); pin.numpy()[:] = buf
 nb = (n + block - 1)//block; stride = T.slot_stride(block); cap = 16 + nb*(stride+3)
 pc = torch.empty(cap, dtype=torch.uint8, pin_memory=True); po = torch.empty(n+128, dtype=torch.uint8, pin_memory=True)

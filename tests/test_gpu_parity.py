@@ -368,27 +368,34 @@ def test_cpp_caller_of_the_reference_api(torch, tmp_path):
 
 
 def test_pipelined_host_path_equals_one_shot(torch, ctx):
-    """The chunked, stream-overlapped host path (H2D | kernels | D2H) must produce the very same container
-    as one-shot staging, including the bytes a chunk's last block reads from the next chunk."""
+    """The stream-overlapped host paths must produce the very same container as one-shot staging, including the bytes a
+    chunk's last block reads from the next chunk: whole chunks on their own streams (H2D | kernels | D2H), and the
+    piece-streamed path, where the encoder starts on a block's first piece and polls for the rest while it runs
+    (tsq_capi.cu compress_streamed; 64 KiB ... 4 MiB blocks, ragged last block, both formats)."""
     ctx.set_option("pipeline_min", 1 << 20)
     try:
-        for kind, n, block in [("text", (5 << 20) + 4321, 65536), ("text", (3 << 20), 4096), ("rep8", (6 << 20) + 1, 1 << 20),
-                               ("random", (2 << 20) + 99, 262144)]:
+        for kind, n, block, ext in [("text", (5 << 20) + 4321, 65536, 0), ("text", (3 << 20), 4096, 0), ("rep8", (6 << 20) + 1, 1 << 20, 0),
+                                    ("random", (2 << 20) + 99, 262144, 0), ("text", (40 << 20) + 4321, 262144, 0), ("text", (48 << 20) + 7, 262144, 1),
+                                    ("text", 64 << 20, 1 << 20, 0), ("random", (24 << 20) + 100000, 262144, 0), ("rep8", (50 << 20) + 5, 1 << 20, 1),
+                                    ("text", (200 << 20) + 1, 4 << 20, 0)]:
             buf = W.fill(kind, n, seed=31)
             ctx.set_option("pipeline", 0)
-            one = ctx.compress_buffer(buf[:n], block, 0)
+            one = ctx.compress_buffer(buf[:n], block, ext)
             ctx.set_option("pipeline", 1)
-            piped = ctx.compress_buffer(buf[:n], block, 0)
-            if piped != one:
-                a, b = np.frombuffer(one, np.uint8), np.frombuffer(piped, np.uint8)
-                m = min(a.size, b.size)
-                bad = np.flatnonzero(a[:m] != b[:m])
-                raise AssertionError((kind, n, block, a.size, b.size, bad[:8].tolist()))
+            for stream_in in (0, 1):
+                ctx.set_option("stream_in", stream_in)
+                piped = ctx.compress_buffer(buf[:n], block, ext)
+                if piped != one:
+                    a, b = np.frombuffer(one, np.uint8), np.frombuffer(piped, np.uint8)
+                    m = min(a.size, b.size)
+                    bad = np.flatnonzero(a[:m] != b[:m])
+                    raise AssertionError((kind, n, block, ext, stream_in, a.size, b.size, bad[:8].tolist()))
             assert ctx.decompress_buffer(piped) == buf[:n].tobytes(), (kind, n, block)
             ctx.set_option("pipeline", 0)
             assert ctx.decompress_buffer(piped) == buf[:n].tobytes()
     finally:
         ctx.set_option("pipeline", 1)
+        ctx.set_option("stream_in", 1)
         ctx.set_option("pipeline_min", 64 << 20)
 
 

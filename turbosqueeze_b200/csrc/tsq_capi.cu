@@ -104,6 +104,12 @@ struct tsqb_context {
     cudaEvent_t ev_in[kPipe] = {}, ev_done[kPipe] = {};
     uint64_t* h_len = nullptr;                 // pinned: per-chunk container length
     int pipeline = 1;                          // 0: one-shot staging (round-1 v1 behaviour)
+    int stream_in = 1;                         // compress: 1 = piece-streamed input (compress_streamed), 0 = whole chunks (option "stream_in")
+    int stream_stagger = 0;                    // compress_streamed: chunk k's kernel starts behind transfer k * stream_stagger (option "stream_stagger";
+                                               // measured 0 / 3 / 5 / 8: 43.3 / 44.9 / 45.6 / 47.0 ms per GB -- starting late only finishes late)
+    std::vector<cudaEvent_t> ev_xfer;          // compress_streamed: one event per (piece, chunk) transfer
+    uint32_t* h_piece = nullptr;               // pinned: the values the arrival flags take
+    DevBuf flags;                              // arrival flags of the chunks + the kernels' error word
     uint64_t pipeline_min = 64ull << 20;       // buffers below this many bytes are staged in one shot
     std::recursive_mutex mtx;          // host entry points hold it across their layer-1 calls
 };
@@ -157,6 +163,9 @@ extern "C" void tsqb_destroy(tsqb_context* c)
         if (c->ev_done[k]) cudaEventDestroy(c->ev_done[k]);
     }
     if (c->h_len) cudaFreeHost(c->h_len);
+    if (c->h_piece) cudaFreeHost(c->h_piece);
+    for (cudaEvent_t e : c->ev_xfer) cudaEventDestroy(e);
+    c->flags.release();
     if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
     delete c;
 }
@@ -179,6 +188,8 @@ extern "C" int tsqb_set_option(tsqb_context* c, const char* key, int64_t v)
     if (!strcmp(key, "pipeline")) { c->pipeline = (int)v; return 0; }
     if (!strcmp(key, "pipeline_min")) { c->pipeline_min = (uint64_t)v; return 0; }
     if (!strcmp(key, "pipe_taper")) { c->pipe_taper = (int)v; return 0; }
+    if (!strcmp(key, "stream_in")) { c->stream_in = (int)v; return 0; }
+    if (!strcmp(key, "stream_stagger")) { if (v < 0 || v > 64) return 1; c->stream_stagger = (int)v; return 0; }
     if (!strcmp(key, "pipe_chunks")) { if (v < 1 || v > tsqb_context::kPipe) return 1; c->pipe_chunks = (int)v; return 0; }
     if (!strcmp(key, "l2_fetch")) {                                  // 32 / 64 / 128: DRAM fetch granularity hint
         cudaSetDevice(c->device);
@@ -209,7 +220,8 @@ static int scratch_release(tsqb_context* c, cudaStream_t st)
 // `tables` (optional): caller-provided region of encode_slots_for(...) tables, for launches that overlap in time
 static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t total, uint32_t block, uint8_t* d_slots,
                               uint64_t stride, uint32_t* d_sizes, uint32_t* d_tailflags, uint32_t with_ext, void* stream,
-                              uint16_t* tables = nullptr, int64_t slot_cap = 0)
+                              uint16_t* tables = nullptr, int64_t slot_cap = 0, const uint32_t* arrived = nullptr,
+                              const uint32_t* arrived_next = nullptr, uint32_t* stream_error = nullptr)
 {
     if (!c) return fail("tsqb_encode_blocks: null context");
     if (block == 0 || block > kBlockMax) return fail("tsqb_encode_blocks: block size %u not in 1..%u", block, kBlockMax);
@@ -222,6 +234,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.in = d_in; a.total = total; a.block = block; a.nb = (total + block - 1) / block;
     a.slots = d_slots; a.stride = stride; a.sizes = d_sizes; a.tailflags = d_tailflags;
     a.hints = (uint32_t)c->encode_hints;
+    a.arrived = arrived; a.arrived_next = arrived_next; a.stream_error = stream_error;
     a.epoch = (++c->launch_id) << 20;                                 // + the slot's block counter, < 2^20
     const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
     a.n_slots = encode_slots_for(impl, a.nb, c->sm_count, slot_cap > 0 ? slot_cap : c->encode_slots);
@@ -525,6 +538,135 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     return 0;
 }
 
+// Piece-streamed compression.  A block's parse is a serial chain that takes ~20 ms however few blocks run, so with whole-chunk
+// staging the job ends one block latency after the LAST byte has crossed PCIe.  Here every block starts as soon as its FIRST
+// piece has landed: the input crosses PCIe piece-major -- piece p of every block of chunk 0, of chunk 1, ... then piece p + 1
+// (strided copies) -- each transfer followed, in stream order, by a 4-byte copy that publishes "bytes of every block's prefix
+// landed" for that chunk; the encoder polls that word before it reads on (EncodeArgs::arrived).  Same bytes as the one-shot
+// path (tests: test_pipelined_host_path_equals_one_shot).  Measured (1 GB, 256 KiB blocks, pinned buffers): 46.4 -> 43.3 ms;
+// what remains is the parse of all blocks (they share the GPU fairly, so they all finish together, ~31 ms) and then the
+// container's trip home (0.62 GB, ~11 ms), which nothing can overlap with: the bytes are not final before the blocks end.
+// Starting the chunks' kernels apart (stream_stagger) does not make them finish apart; it only delays the last one.
+// Returns -1 when the shape does not suit it (small or odd block sizes, few blocks): the caller takes the chunked path.
+static int compress_streamed(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n, uint32_t block,
+                             uint32_t with_ext, uint8_t* host_out, uint64_t host_cap, uint8_t** out, uint64_t* out_size,
+                             const ProgressFn* prog)
+{
+    constexpr int KMAX = tsqb_context::kPipe, P = 8;
+    const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
+    const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
+    if (impl != 3 || block < 65536u || (block % (P * 256u)) != 0 || c->encode_slots > 0 || c->encode_fat == 0) return -1;
+    int K = c->pipe_chunks;
+    if (nb < (uint64_t)K * 8u) return -1;
+    const uint32_t S = block / P;
+    uint64_t cb[KMAX + 1];
+    for (int k = 0; k <= K; k++) cb[k] = nb * k / K;
+    uint64_t per = 0;
+    for (int k = 0; k < K; k++) if (cb[k + 1] - cb[k] > per) per = cb[k + 1] - cb[k];
+    // every block in flight: one table per block (as the chunked path provisions them, a full grid in all)
+    uint64_t tab_at[KMAX], tab_total = 0;
+    for (int k = 0; k < K; k++) { tab_at[k] = tab_total; tab_total += cb[k + 1] - cb[k]; }
+    if (tab_total > (uint64_t)c->sm_count * 32u) return -1;                   // more blocks than resident warps: chunked path
+    const uint64_t ccap = 16 + per * (stride + 3) + 256;
+    if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
+        c->cont.ensure(ccap * K) || c->offs.ensure((nb + KMAX) * 8) || c->misc.ensure(64 * KMAX) || c->flags.ensure(256) ||
+        c->ftables.ensure(tab_total * kFatTableBytes))
+        return fail("compress: out of device memory");
+    if (!c->h_piece) {
+        if (cudaMallocHost((void**)&c->h_piece, sizeof(uint32_t) * (P + 1)) != cudaSuccess) { cudaGetLastError(); return -1; }
+    }
+    for (int p = 0; p < P; p++) c->h_piece[p] = (uint32_t)(p + 1) * S;
+    while (c->ev_xfer.size() < (size_t)P * KMAX) {
+        cudaEvent_t e;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+        c->ev_xfer.push_back(e);
+    }
+#define CUP(call)                                                                                  \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) { cudaDeviceSynchronize(); return fail("%s: %s", #call, cudaGetErrorString(e_)); } \
+    } while (0)
+    uint8_t* d_in = (uint8_t*)c->in.p;
+    uint32_t* d_flags = (uint32_t*)c->flags.p;                                // [0..K) arrival flags, [32] error word
+    CUP(cudaMemsetAsync(d_flags, 0, 256, c->s_in));
+    CUP(cudaMemsetAsync(d_in + total, 0, 2 * TSQB_INPUT_PAD, c->s_in));
+    if (tail && tail_n) CUP(cudaMemcpyAsync(d_in + total, tail, tail_n, cudaMemcpyHostToDevice, c->s_in));
+    // ---- the input, piece-major
+    const uint64_t nfull = total / block;                                     // blocks that are complete
+    for (int p = 0; p < P; p++)
+        for (int k = 0; k < K; k++) {
+            const uint64_t b0 = cb[k], b1 = cb[k + 1];
+            const uint64_t rows = (b1 <= nfull ? b1 : nfull) > b0 ? (b1 <= nfull ? b1 : nfull) - b0 : 0;
+            const uint64_t at = b0 * (uint64_t)block + (uint64_t)p * S;
+            if (rows) CUP(cudaMemcpy2DAsync(d_in + at, block, in + at, block, S, rows, cudaMemcpyHostToDevice, c->s_in));
+            if (b1 > nfull && nfull >= b0) {                                  // the ragged last block: what it has of this piece
+                const uint64_t lo = nfull * (uint64_t)block + (uint64_t)p * S;
+                const uint64_t hi = lo + S < total ? lo + S : total;
+                if (lo < hi) CUP(cudaMemcpyAsync(d_in + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->s_in));
+            }
+            CUP(cudaMemcpyAsync(d_flags + k, &c->h_piece[p], 4, cudaMemcpyHostToDevice, c->s_in));
+            CUP(cudaEventRecord(c->ev_xfer[p * K + k], c->s_in));
+        }
+    // ---- the kernels: chunk k starts behind transfer k * stagger (never before its own first piece)
+    for (int k = 0; k < K; k++) {
+        const uint64_t b0 = cb[k], b1 = cb[k + 1];
+        const uint64_t lo = b0 * block, hi = (b1 * block < total) ? b1 * block : total;
+        int after = k * c->stream_stagger;
+        if (after < k) after = k;
+        if (after > P * K - 1) after = P * K - 1;
+        cudaStream_t st = c->s_chunk[k];
+        CUP(cudaStreamWaitEvent(st, c->ev_xfer[after], 0));
+        CUP(cudaMemsetAsync((uint8_t*)c->slots.p + b0 * stride, 0, (b1 - b0) * stride, st));   // zero-filled slots (parity contract)
+        if (encode_blocks_impl(c, d_in + lo, hi - lo, block, (uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, nullptr, with_ext,
+                               st, (uint16_t*)((uint8_t*)c->ftables.p + tab_at[k] * kFatTableBytes), (int64_t)(b1 - b0), d_flags + k,
+                               k + 1 < K ? d_flags + k + 1 : nullptr, d_flags + 32)) { cudaDeviceSynchronize(); return 1; }
+        uint8_t* d_cont = (uint8_t*)c->cont.p + (uint64_t)k * ccap;
+        uint64_t* d_len = (uint64_t*)c->misc.p + 8 * k;
+        CUP(launch_pack((uint8_t*)c->slots.p + b0 * stride, stride, (uint32_t*)c->sizes.p + b0, b1 - b0, hi - lo, with_ext, d_cont, d_len,
+                        (uint64_t*)c->offs.p + b0 + k, st));
+        g_launches += 2;
+        CUP(cudaMemcpyAsync(&c->h_len[k], d_len, 8, cudaMemcpyDeviceToHost, st));
+        CUP(cudaEventRecord(c->ev_done[k], st));
+    }
+#undef CUP
+    // ---- results leave in order; the body of chunk k goes behind the bodies before it
+    uint8_t* host = host_out;
+    if (!host) {
+        host = (uint8_t*)malloc(16 + nb * (stride + 3));
+        if (!host) { cudaDeviceSynchronize(); return fail("compress: malloc failed"); }
+    }
+    uint64_t at = 16;
+    cudaError_t err = cudaSuccess;
+    bool too_small = false;
+    for (int k = 0; k < K && err == cudaSuccess && !too_small; k++) {
+        err = cudaEventSynchronize(c->ev_done[k]);
+        if (err != cudaSuccess) break;
+        const uint64_t body = c->h_len[k] - 16;
+        if (host_out && at + body > host_cap) { too_small = true; break; }
+        err = cudaMemcpyAsync(host + at, (uint8_t*)c->cont.p + (uint64_t)k * ccap + 16, body, cudaMemcpyDeviceToHost, c->s_out);
+        at += body;
+        report_blocks(prog, cb[k], k + 1 == K ? nb - 1 : cb[k + 1], nb);
+    }
+    uint32_t stream_err = 0;
+    if (err == cudaSuccess) err = cudaStreamSynchronize(c->s_out);
+    if (err == cudaSuccess) err = cudaMemcpy(&stream_err, d_flags + 32, 4, cudaMemcpyDeviceToHost);
+    if (err != cudaSuccess || too_small || stream_err) {
+        cudaDeviceSynchronize();
+        if (!host_out) free(host);
+        if (too_small) return fail("compress: output needs more than the %llu bytes the caller gave", (unsigned long long)host_cap);
+        if (stream_err) return fail("compress: the encoder timed out waiting for its input to arrive");
+        return fail("compress: %s", cudaGetErrorString(err));
+    }
+    memcpy(host, "TSQ1", 4);                                                  // turbosqueeze.cpp:64-67
+    const uint32_t nb32 = (uint32_t)nb;
+    memcpy(host + 4, &nb32, 4);
+    memcpy(host + 8, &total, 8);
+    if (nb) report_blocks(prog, nb - 1, nb, nb);
+    if (out) *out = host;
+    *out_size = at;
+    return 0;
+}
+
 // Container in host memory: the u24 chain is walked on the host (it is serial by construction,
 // tsq_threads.cpp:480-484, and the bytes are right here), then chunks of blocks are copied, decoded and
 // copied back on separate streams.  Returns 1 with g_err set on failure, -1 when the container is not
@@ -612,8 +754,13 @@ static int compress_any(tsqb_context* c, const uint8_t* in, uint64_t total, cons
 {
     std::lock_guard<std::recursive_mutex> lk(c->mtx);
     CU(cudaSetDevice(c->device));
-    if (c->pipeline && total >= c->pipeline_min)
+    if (c->pipeline && total >= c->pipeline_min) {
+        if (c->stream_in) {
+            const int r = compress_streamed(c, in, total, tail, tail_n, block, with_ext, host_out, host_cap, out, out_size, prog);
+            if (r >= 0) return r;
+        }
         return compress_pipelined(c, in, total, tail, tail_n, block, with_ext, host_out, host_cap, out, out_size, prog);
+    }
     return compress_locked(c, in, total, tail, tail_n, block, with_ext, host_out, host_cap, out, out_size, prog);
 }
 

@@ -24,6 +24,13 @@ struct EncodeArgs {
     uint64_t       epoch;     // batch encoder: entries written under another epoch are empty (no per-block zeroing)
     uint32_t       fat;       // batch encoder: 1 = sector entries (kFatTableBytes per table), 0 = u16 tables
     uint32_t       n_slots;
+    // Piece-streamed input (host path, tsq_capi.cu compress_streamed): the bytes of the blocks arrive over PCIe WHILE the kernel
+    // runs, the same prefix of every block at a time.  *arrived = bytes of each block's prefix that have landed (written by a
+    // stream-ordered copy behind the data); *arrived_next = the same for the blocks that follow this launch's last block, whose
+    // first bytes that block reads (nullptr: nothing follows but the zero pad); *stream_error is set when a wait times out.
+    const uint32_t* arrived = nullptr;
+    const uint32_t* arrived_next = nullptr;
+    uint32_t*      stream_error = nullptr;
     uint32_t       hints = 0; // batch encoder experiments (only in a build with -DTSQB_ENC_HINTS=1; ignored otherwise):
                               // 1 = table traffic evict-first in L2, 2 = streaming output stores, 4 / 8 = L2 prefetches
 };

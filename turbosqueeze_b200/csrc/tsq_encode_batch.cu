@@ -185,6 +185,21 @@ __device__ __forceinline__ uint32_t lanes_from_to(uint32_t lo, uint32_t hi)   //
     return ((2u << hi) - 1u) & ~((1u << lo) - 1u);
 }
 
+// Piece-streamed input: wait until `want` bytes of the block's prefix have landed.  The flag is written by a copy that is
+// stream-ordered behind the data, and read around L1; the loads that follow are issued after the branch on its value.
+// A wait that lasts seconds means the host side died: report it and carry on (the call fails) instead of hanging the GPU.
+__device__ __forceinline__ uint32_t wait_arrived(const uint32_t* flag, uint32_t want, uint32_t* err)
+{
+    uint32_t v;
+    const long long t0 = clock64();
+    for (;;) {
+        asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+        if (v >= want) return v;
+        __nanosleep(500);
+        if (clock64() - t0 > 6000000000ll) { *err = 1u; return 0xFFFFFFFFu; }
+    }
+}
+
 struct BlockEncoder {
     // ---- fixed for the block
     const uint8_t* __restrict__ in;
@@ -386,9 +401,12 @@ struct BlockEncoder {
 // FAT = sector entries in a 4 MiB table (thousands of blocks in flight: the tables live in HBM and a probe must
 // not need a second, dependent access); !FAT = the reference's own 2^17 x u16 table, zeroed per block, for a few
 // hundred blocks in flight, whose tables (256 KiB each) and 64 KiB back-windows stay resident in the 126 MB L2.
-template <bool FAT, bool EXT>
+// STREAM (sector entries only): the block's bytes arrive while it is being encoded (EncodeArgs::arrived); the alias tags,
+// which read up to 192 KiB ahead of the scan, are left out -- an aged entry is then answered by reading the candidate's bytes.
+template <bool FAT, bool EXT, bool STREAM>
 __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t epoch, const uint8_t* __restrict__ in, const uint32_t size,
-                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags, const uint32_t hints_)
+                                       uint8_t* __restrict__ out, const unsigned lane, WarpWs& ws, uint32_t& flags, const uint32_t hints_,
+                                       const uint32_t* arrived = nullptr, const uint32_t* arrived_next = nullptr, uint32_t* stream_error = nullptr)
 {
     const uint32_t hints = TSQB_ENC_HINTS ? hints_ : 0u;
     uint64_t pol = 0;                                                  // experiment: table traffic marked evict-first in L2
@@ -415,7 +433,16 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
     bool chain_pending = false;       // the next probe is a post-match probe (:162-170)
     uint32_t c0 = 0;                  // lane of the window's first probe (fixed grid: the parse may enter a window anywhere)
 
+    uint32_t landed = 0;              // STREAM: bytes of this block known to have arrived
+    bool next_ok = arrived_next == nullptr;
     for (;;) {                                                         // one window per iteration
+        if constexpr (STREAM) {
+            // everything this window can read: the lanes' 16 bytes (x + 19), a match attempt (i + 64), a literal run's blind
+            // 16 bytes -- all below base + 128.  Past the block's end that is the first bytes of the block behind it.
+            const uint32_t need = base + 128u;
+            if (min(need, size) > landed) landed = wait_arrived(arrived, min(need, size), stream_error);
+            if (need > size && !next_ok) { wait_arrived(arrived_next, 128u, stream_error); next_ok = true; }
+        }
         // ---------------- window precompute (parallel over 32 positions)
         const uint32_t x = base + lane;
         uint32_t own[4], cb[4];
@@ -425,7 +452,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
         // alias tags for this position's own entry, should it be committed: loaded now, with everything else of the
         // window (sequential streams 64 / 128 / 192 KiB ahead of the scan), so that the commit waits for nothing
         uint32_t a1 = 0, a2 = 0, a3 = 0;
-        if constexpr (FAT) {
+        if constexpr (FAT && !STREAM) {
             if (x + 65536u < size)  a1 = tag_at(in, x + 65536u);
             if (x + 131072u < size) a2 = tag_at(in, x + 131072u);
             if (x + 196608u < size) a3 = tag_at(in, x + 196608u);
@@ -450,7 +477,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
                 const uint32_t seg = live ? (tab_cand - p22) >> 16 : 0u;
                 const uint32_t atag = seg == 1u ? (A.y >> 5) : (seg == 2u ? B.w : (B.w >> 15));
                 constexpr uint32_t kAliasMask = TSQB_ENC_ALIAS8 ? 0x7F80u : 0x7FFFu;
-                if (seg - 1u < 3u && ((atag ^ (w >> 17)) & kAliasMask) != 0u) m_tab = 0u;   // different words: the probe fails (:100)
+                if (!STREAM && seg - 1u < 3u && ((atag ^ (w >> 17)) & kAliasMask) != 0u) m_tab = 0u;   // different words: the probe fails (:100)
                 else {
                     ldg16(in + tab_cand, cb);
                     m_tab = prefix16(own, cb);                         // >= 4  <=>  the 4-byte words are equal (:100)
@@ -676,7 +703,7 @@ __device__ uint32_t encode_block_batch(void* __restrict__ table_, const uint64_t
     return e.finish(flags);
 }
 
-template <bool FAT, bool EXT>
+template <bool FAT, bool EXT, bool STREAM = false>
 __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
 {
     __shared__ WarpWs ws_all[kWarps];
@@ -701,7 +728,9 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
         const uint64_t at = b * (uint64_t)a.block;
         const uint32_t n = (uint32_t)((a.total - at < a.block) ? a.total - at : a.block);
         uint32_t flags;
-        const uint32_t c = encode_block_batch<FAT, EXT>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags, a.hints);
+        // (streamed input: what follows the launch's last block belongs to the next launch's blocks)
+        const uint32_t c = encode_block_batch<FAT, EXT, STREAM>(table, epoch, a.in + at, n, a.slots + b * a.stride, lane, ws, flags, a.hints, a.arrived,
+                                                                b + 1 == a.nb ? a.arrived_next : nullptr, a.stream_error);
         if (lane == 0) { a.sizes[b] = c; if (a.tailflags) a.tailflags[b] = flags; }
         __syncwarp();
     }
@@ -713,7 +742,11 @@ cudaError_t launch_encode_batch(const EncodeArgs& a, bool ext, cudaStream_t st)
 {
     if (a.nb == 0) return cudaSuccess;
     const unsigned ctas = (a.n_slots + kWarps - 1) / kWarps;
-    if (ext) {
+    if (a.arrived) {                                                   // piece-streamed input: sector entries only
+        if (!a.fat) return cudaErrorInvalidValue;
+        if (ext) encode_batch_kernel<true, true, true><<<ctas, kWarps * 32, 0, st>>>(a);
+        else     encode_batch_kernel<true, false, true><<<ctas, kWarps * 32, 0, st>>>(a);
+    } else if (ext) {
         if (a.fat) encode_batch_kernel<true, true><<<ctas, kWarps * 32, 0, st>>>(a);
         else       encode_batch_kernel<false, true><<<ctas, kWarps * 32, 0, st>>>(a);
     } else {
