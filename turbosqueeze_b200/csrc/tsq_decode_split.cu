@@ -60,8 +60,11 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_FLUSH2
 #define TSQB_DEC_FLUSH2 1          // lane-per-pair copier: flush of a step = two predicated 128-bit moves (a step leaves <= 65 units)
 #endif
+#ifndef TSQB_DEC_DIAG
+#define TSQB_DEC_DIAG 0            // timing diagnostic, WRONG OUTPUT: 1 = the lane-per-pair copier moves no bytes (walker + hand-over + flush only)
+#endif
 #ifndef TSQB_DEC_WMASK
-#define TSQB_DEC_WMASK 1           // walker: the 4-group path masks its ring addresses instead of requiring that it does not wrap
+#define TSQB_DEC_WMASK 0           // walker: 1 = the 4-group path masks its ring addresses instead of requiring that it does not wrap (2.615 vs 2.600 ms: no gain)
 #endif
 constexpr uint32_t kQueue    = TSQB_DEC_QUEUE;       // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
@@ -833,6 +836,7 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                 const bool now0 = act0 && (l0 || src0 + len0 <= J0), now1 = act1 && (l1 || src1 + len1 <= J0);
                 const bool pend0 = act0 && !now0, pend1 = act1 && !now1;
                 const bool far0 = now0 && !l0 && src0 + OUT_RING < J1 + 16u, far1 = now1 && !l1 && src1 + OUT_RING < J1 + 16u;
+#if TSQB_DEC_DIAG != 1
                 uint32_t w0[5], w1[5];
 #if TSQB_DEC_FARWIDE
                 uint4 fa0, fb0, fa1, fb1;
@@ -909,6 +913,9 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                     copy_in_order(s_q, s_src, s_len);
                     if (first) pm0 &= ~(1u << pl); else pm1 &= ~(1u << pl);
                 }
+#endif
+#else
+                (void)far0; (void)far1; (void)pend0; (void)pend1;
 #endif
                 __syncwarp();
                 if (F & 15u) flush(J1, false); else if ((J1 & ~15u) > F) flush_units(J1 & ~15u);
