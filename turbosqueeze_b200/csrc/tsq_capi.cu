@@ -719,10 +719,27 @@ static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_
         c->out.ensure(nb * (uint64_t)block)) { fail("decompress: out of device memory"); return bail(1); }
     CUP(cudaMemcpyAsync(c->offs.p, offs.data(), nb * 8, cudaMemcpyHostToDevice, c->s_in));
     CUP(cudaMemcpyAsync(c->sizes.p, sizes.data(), nb * 4, cudaMemcpyHostToDevice, c->s_in));
-    const uint64_t per = (nb + K - 1) / K;
-    const int nchunks = (int)((nb + per - 1) / per);
+    // Chunk boundaries: the output's trip home (U bytes of D2H) is the long leg and can only start once the first chunk
+    // is decoded, so the first chunks are small (1 : 2 : 4 : 8 : 8 : ...) and the D2H stream starts ~1.5 ms earlier.
+    constexpr int KMAX = tsqb_context::kPipe;
+    uint64_t cbd[KMAX + 1];
+    int nchunks = 0;
+    {
+        int want = K + 2 > KMAX ? KMAX : K + 2;
+        double w[KMAX], sum = 0;
+        for (int k = 0; k < want; k++) { w[k] = k < 3 ? (double)(1 << k) : 8.0; sum += w[k]; }
+        double acc = 0;
+        cbd[0] = 0;
+        for (int k = 0; k < want; k++) {
+            acc += w[k];
+            uint64_t e = k == want - 1 ? nb : (uint64_t)(nb * (acc / sum) + 0.5);
+            if (e > nb) e = nb;
+            if (e > cbd[nchunks]) cbd[++nchunks] = e;
+        }
+        if (cbd[nchunks] < nb) cbd[nchunks] = nb;
+    }
     for (int k = 0; k < nchunks; k++) {
-        const uint64_t b0 = k * per, b1 = (b0 + per < nb) ? b0 + per : nb;
+        const uint64_t b0 = cbd[k], b1 = cbd[k + 1];
         const uint64_t lo = offs[b0], hi = offs[b1 - 1] + sizes[b1 - 1];
         CUP(cudaMemcpyAsync((uint8_t*)c->cont.p + lo, in + lo, hi - lo, cudaMemcpyHostToDevice, c->s_in));
         CUP(cudaEventRecord(c->ev_in[k], c->s_in));
@@ -738,7 +755,7 @@ static int decompress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t in_
     }
     for (int k = 0; k < nchunks; k++) {                                       // progress, chunk by chunk as the output lands
         CUP(cudaEventSynchronize(c->ev_in[k]));
-        report_blocks(prog, k * per, ((k + 1) * per < nb) ? (k + 1) * per : nb, nb);
+        report_blocks(prog, cbd[k], cbd[k + 1], nb);
     }
     CUP(cudaStreamSynchronize(c->s_out));
 #undef CUP
