@@ -405,29 +405,41 @@ def time_gather(env, ctx, wl, res, n, block, nb_total, total_all):
     torch, dist = env.torch, env.dist
     state = {}
 
-    def gather_step():
+    def gather_step(transport):
         cont, clen = ctx.pack_container(res["slots"], res["sizes"], block, n)
         state["cont"], state["clen"] = cont, clen
-        return S.gather_container(cont, total_all, nb_total, dst=0, length=clen)
+        return S.gather_container(cont, total_all, nb_total, dst=0, length=clen, transport=transport)
 
-    gather_step()
-    env.barrier()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record()
-    gathered = gather_step()
-    g1.record()
-    env.barrier()
-    ms = env.reduce([g0.elapsed_time(g1)], "MAX")[0]
-    body = env.reduce([float(int(state["clen"].item()) - 16)], "SUM")[0]
+    times, gathered = {}, None
+    for transport in ("nccl", "peer"):                              # "peer" last: its container is the one checked below
+        del gathered
+        gathered = gather_step(transport)
+        env.barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        del gathered
+        gathered = gather_step(transport)
+        g1.record()
+        env.barrier()
+        times[transport] = env.reduce([g0.elapsed_time(g1)], "MAX")[0]
+    ms = times["peer"]
+    mine = int(state["clen"].item()) - 16
+    body = env.reduce([float(mine)], "SUM")[0]
+    # every rank's body must have arrived: sum of all bytes (the byte-exact check is tests/test_sharded_gpu.py)
+    t = torch.stack([state["cont"][16:16 + mine].sum(dtype=torch.int64)])
+    if env.world > 1:
+        dist.all_reduce(t)
     out = None
     if env.rank == 0:
         hdr = bytes(gathered[:16].cpu().numpy())
-        mine = int(state["clen"].item()) - 16
         ok = (hdr[:4] == b"TSQ1" and int.from_bytes(hdr[4:8], "little") == nb_total and int.from_bytes(hdr[8:16], "little") == total_all and
-              int(gathered.numel()) == 16 + int(body) and bool(torch.equal(gathered[16:16 + mine], state["cont"][16:16 + mine])))
+              int(gathered.numel()) == 16 + int(body) and bool(torch.equal(gathered[16:16 + mine], state["cont"][16:16 + mine])) and
+              int(gathered[16:].sum(dtype=torch.int64).item()) == int(t[0].item()))
         out = {"ms": round(ms, 3), "container_bytes": int(gathered.numel()), "ok": ok, "root_ingress_gbs": round((body - mine) / (ms * 1e-3) / 1e9, 1),
-               "what": "tsqb_pack_container per rank + one all_gather of the device-side byte counts (one host sync) + grouped NCCL "
-                       "send/recv straight into the root's container"}
+               "ms_nccl_send_recv": round(times["nccl"], 3), "root_ingress_gbs_nccl_send_recv": round((body - mine) / (times["nccl"] * 1e-3) / 1e9, 1),
+               "what": "tsqb_pack_container per rank + one all_gather of the device-side byte counts (one host sync) + every rank writes its "
+                       "body straight into the root's container through peer memory (CUDA IPC mapping, one device-to-device copy over "
+                       "NVLink / NVSwitch per rank); ms_nccl_send_recv = the same with grouped NCCL send/recv"}
         if wl["split"] == "sharded":
             out["note"] = ("sharded stream: the gathered container IS the container of the whole stream "
                            "(tests/test_sharded_gpu.py checks it against the single-GPU container and the reference)")

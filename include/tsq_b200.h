@@ -137,6 +137,16 @@ int tsqb_index_container(tsqb_context* ctx, const uint8_t* d_container, uint64_t
                          uint64_t max_blocks, uint64_t* d_offsets, uint32_t* d_sizes,
                          uint32_t* d_ext_flags, uint64_t* d_n_blocks, void* stream);
 
+/* Peer memory for the multi-GPU gather (one process per GPU; not in the reference, which has no devices).  The root rank
+ * exports the buffer that receives the container (tsqb_ipc_export: 64-byte CUDA IPC handle of the allocation + the
+ * pointer's offset inside it), every other rank maps it (tsqb_ipc_open -> base pointer in its own address space) and
+ * copies its bytes to base + offset + its prefix-summed position with tsqb_copy_d2d (asynchronous on `stream`, over
+ * NVLink / NVSwitch), then unmaps it (tsqb_ipc_close).  turbosqueeze_b200/sharding.py is the caller. */
+int tsqb_ipc_export(const void* d_ptr, uint8_t handle[64], uint64_t* offset);
+int tsqb_ipc_open(const uint8_t handle[64], void** base);
+int tsqb_ipc_close(void* base);
+int tsqb_copy_d2d(void* dst, const void* src, uint64_t n, void* stream);
+
 /* Host-buffer convenience used by the reference-style entry points and the end-to-end benchmark:
  * H2D, tsqb_encode_blocks, D2H of sizes and of the slots' used bytes, inside one call.
  *   in        host pointer (pageable or pinned), `total` bytes; the library pads on the device

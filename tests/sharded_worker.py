@@ -35,7 +35,9 @@ def main():
     ctx = T.Context(local)
     buf = W.fill(kind, total, seed=4242)                          # every rank generates the same stream, reads its own range
     nb = (total + block - 1) // block
-    cont, info = S.encode_sharded(ctx, buf, total, block, ext, dst=0)
+    # both transports of the gather: peer-memory writes (the default under NCCL) and grouped NCCL send/recv
+    cont_nccl, _ = S.encode_sharded(ctx, buf, total, block, ext, dst=0, transport="nccl")
+    cont, info = S.encode_sharded(ctx, buf, total, block, ext, dst=0, transport="peer")
     torch.cuda.synchronize()
     res = {"world": world, "kind": kind, "total": total, "block": block, "ext": ext, "n_blocks": nb}
     ok = True
@@ -47,6 +49,7 @@ def main():
         one, n1 = ctx.pack_container(slots, sizes, block, total, ext)
         one = one[: int(n1.item())].cpu().numpy()
         res["equals_single_gpu_container"] = bool(got.size == one.size and np.array_equal(got, one))
+        res["transports_agree"] = bool(torch.equal(cont, cont_nccl))
         # (b) the reference's streams
         codec = best_cpu_codec()
         res["checker"] = codec.name
@@ -65,7 +68,7 @@ def main():
                 res["first_bad_block"] = b
                 break
         res["equals_reference_streams"] = bool(same and at == got.size)
-        ok = res["equals_single_gpu_container"] and res["equals_reference_streams"]
+        ok = res["equals_single_gpu_container"] and res["equals_reference_streams"] and res["transports_agree"]
     # (c) decode, sharded: rank r indexes the container (rank 0 broadcasts it) and decodes its own block range
     n_t = torch.tensor([cont.numel() if rank == 0 else 0], dtype=torch.int64, device="cuda")
     dist.broadcast(n_t, 0)

@@ -68,6 +68,10 @@ def library(path=None):
     L.tsqb_decompress_buffer.argtypes = [_vp, _vp, C.c_uint64, C.POINTER(_vp), C.POINTER(C.c_uint64)]
     L.tsqb_compress_into.argtypes = [_vp, _vp, C.c_uint64, C.c_uint32, C.c_uint32, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
     L.tsqb_decompress_into.argtypes = [_vp, _vp, C.c_uint64, _vp, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.tsqb_ipc_export.argtypes = [_vp, _vp, C.POINTER(C.c_uint64)]
+    L.tsqb_ipc_open.argtypes = [_vp, C.POINTER(_vp)]
+    L.tsqb_ipc_close.argtypes = [_vp]
+    L.tsqb_copy_d2d.argtypes = [_vp, _vp, C.c_uint64, _vp]
     L.tsqAllocateContext.restype = _vp
     L.tsqDeallocateContext.argtypes = [_vp]
     L.tsqDeallocateContext.restype = None
@@ -120,6 +124,30 @@ def _as_np(data):
     if isinstance(data, np.ndarray):
         return np.ascontiguousarray(data, dtype=np.uint8)
     return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+# ---- peer memory for the multi-GPU gather (sharding.py) --------------------------------------------------
+def ipc_export(d_ptr):
+    """(64-byte CUDA IPC handle of the allocation d_ptr lies in, d_ptr's offset inside it)."""
+    h = (C.c_uint8 * 64)()
+    off = C.c_uint64(0)
+    _check(library().tsqb_ipc_export(d_ptr, h, C.byref(off)), "tsqb_ipc_export")
+    return bytes(h), off.value
+
+
+def ipc_open(handle):
+    base = _vp()
+    buf = (C.c_uint8 * 64).from_buffer_copy(handle)
+    _check(library().tsqb_ipc_open(buf, C.byref(base)), "tsqb_ipc_open")
+    return base.value
+
+
+def ipc_close(base):
+    _check(library().tsqb_ipc_close(base), "tsqb_ipc_close")
+
+
+def copy_d2d(dst_ptr, src_ptr, n, stream=None):
+    _check(library().tsqb_copy_d2d(dst_ptr, src_ptr, n, _stream_handle(stream)), "tsqb_copy_d2d")
 
 
 class Context:

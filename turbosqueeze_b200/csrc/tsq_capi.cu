@@ -311,6 +311,55 @@ extern "C" int tsqb_index_container(tsqb_context* c, const uint8_t* d_container,
     return 0;
 }
 
+// ------------------------------------------------------------------ peer memory (multi-GPU gather, one process per GPU)
+// The one exchange step of the path is the gather of the per-rank streams into ONE container on the root GPU
+// (SURVEY.md 8(e)).  Instead of NCCL send/recv (staged through NCCL's channel buffers, ~320 GB/s into the root with seven
+// senders), every rank writes its bytes straight into the root's buffer over NVLink / NVSwitch: the root exports its
+// buffer as a CUDA IPC handle, the peers map it and issue one device-to-device copy each at their prefix-summed offset.
+// These four calls are that plumbing, nothing else.
+extern "C" int tsqb_ipc_export(const void* d_ptr, uint8_t handle[64], uint64_t* offset)
+{
+    if (!d_ptr || !handle || !offset) return fail("tsqb_ipc_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    // An IPC handle names a whole allocation: find its base (the pointer may sit inside a caching allocator's segment).
+    typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    CU(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) return fail("tsqb_ipc_export: cuMemGetAddressRange is not available");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (((GetRange)fn)(&base, &size, (unsigned long long)(uintptr_t)d_ptr) != 0) return fail("tsqb_ipc_export: not a device allocation");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, (void*)(uintptr_t)base));
+    memcpy(handle, &h, 64);
+    *offset = (uint64_t)((uintptr_t)d_ptr - (uintptr_t)base);
+    return 0;
+}
+
+extern "C" int tsqb_ipc_open(const uint8_t handle[64], void** base)
+{
+    if (!handle || !base) return fail("tsqb_ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(base, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+
+extern "C" int tsqb_ipc_close(void* base)
+{
+    if (!base) return 0;
+    CU(cudaIpcCloseMemHandle(base));
+    return 0;
+}
+
+extern "C" int tsqb_copy_d2d(void* dst, const void* src, uint64_t n, void* stream)
+{
+    if (n == 0) return 0;
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, (cudaStream_t)stream));    // unified addressing: works for peer memory
+    return 0;
+}
+
 // --------------------------------------------------------------------------- host-buffer convenience
 // `tail` (optional, <= TSQB_INPUT_PAD bytes) are the bytes that follow the input in the caller's memory.
 static int stage_input(tsqb_context* c, const uint8_t* in, uint64_t total, const uint8_t* tail, uint32_t tail_n)
@@ -556,6 +605,8 @@ static int compress_streamed(tsqb_context* c, const uint8_t* in, uint64_t total,
     const int impl = c->encode_impl == 1 ? 1 : ((c->encode_impl == 2 && !with_ext) ? 2 : 3);
     const uint64_t nb = (total + block - 1) / block, stride = tsqb_slot_stride(block);
     if (impl != 3 || block < 65536u || (block % (P * 256u)) != 0 || c->encode_slots > 0 || c->encode_fat == 0) return -1;
+    // the kernels wait for their input with a ~10 s bail-out: keep the whole transfer far below that even from pageable memory
+    if (total > (4ull << 30)) return -1;
     int K = c->pipe_chunks;
     if (nb < (uint64_t)K * 8u) return -1;
     const uint32_t S = block / P;

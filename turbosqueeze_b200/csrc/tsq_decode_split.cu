@@ -60,6 +60,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_FLUSH2
 #define TSQB_DEC_FLUSH2 1          // lane-per-pair copier: flush of a step = two predicated 128-bit moves (a step leaves <= 65 units)
 #endif
+#ifndef TSQB_DEC_DESC2
+#define TSQB_DEC_DESC2 1           // descriptor carries the group's whole control byte (the copier lane picks its pair's two bits from its own
+#endif                             // index) and the walker publishes `produced` once per step: fewer walker instructions per pair
 #ifndef TSQB_DEC_DIAG
 #define TSQB_DEC_DIAG 0            // timing diagnostic, WRONG OUTPUT: 1 = the lane-per-pair copier moves no bytes (walker + hand-over + flush only)
 #endif
@@ -262,10 +265,15 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                         const uint32_t dsl = dbase + ((k & kQMask) << 3);
                         const uint32_t c = lds_u8(pr);
                         uint32_t prp = pr + 1u;
+                        const uint32_t c24 = c << 24;
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t nib = lds_u8(prp);
+#if TSQB_DEC_DESC2
+                            put_desc(dsl + 8u * q, (prp + dlt) | c24, j);
+#else
                             put_desc(dsl + 8u * q, (prp + dlt) | ((c << (18 + 2 * q)) & 0x3000000u), j);
+#endif
                             const uint32_t n0 = nib >> 4, n1 = nib & 15u;
                             const uint32_t pay0 = (c & (0x80u >> (2 * q))) ? n0 + 2u : 3u;
                             const uint32_t pay1 = (c & (0x40u >> (2 * q))) ? n1 + 1u : 2u;
@@ -274,8 +282,12 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                         }
                         pr = prp;
                         k += 4u;
+#if TSQB_DEC_DESC2
+                        if ((k & pmask) == 0) { st_vol_u32(&sm.produced, k); mbar_arrive(&sm.full[steps & smask]); steps++; }
+#else
                         st_vol_u32(&sm.produced, k);
                         if ((k & pmask) == 0) { mbar_arrive(&sm.full[steps & smask]); steps++; }
+#endif
                     }
                     p = pr + dlt;
                     continue;
@@ -289,7 +301,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const uint32_t nib = ring_u8(pp);                           // :68
-                        put_desc(dsl + 8u * q, pp | ((c << (18 + 2 * q)) & 0x3000000u), j);
+                        put_desc(dsl + 8u * q, pp | (TSQB_DEC_DESC2 ? (c << 24) : ((c << (18 + 2 * q)) & 0x3000000u)), j);
                         const uint32_t n0 = nib >> 4, n1 = nib & 15u;
                         const uint32_t pay0 = (c & (0x80u >> (2 * q))) ? n0 + 2u : 3u;   // payload + the size byte itself
                         const uint32_t pay1 = (c & (0x40u >> (2 * q))) ? n1 + 1u : 2u;
@@ -312,7 +324,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     const uint32_t q = k & 3u;
                     if (q == 0) { ctl = ring_u8(pp); pp++; }
                     const uint32_t nib = ring_u8(pp);
-                    put_desc(dbase + ((k & kQMask) << 3), pp | ((ctl << (18u + 2u * q)) & 0x3000000u), j);
+                    put_desc(dbase + ((k & kQMask) << 3), pp | (TSQB_DEC_DESC2 ? (ctl << 24) : ((ctl << (18u + 2u * q)) & 0x3000000u)), j);
                     const uint32_t n0 = nib >> 4, n1 = nib & 15u;
                     const uint32_t pay0 = (ctl & (0x80u >> (2u * q))) ? n0 + 1u : 2u;
                     const uint32_t pay1 = (ctl & (0x40u >> (2u * q))) ? n1 + 1u : 2u;
@@ -324,6 +336,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     st_vol_u32(&sm.produced, k);
                     if ((k & pmask) == 0) { mbar_arrive(&sm.full[steps & smask]); steps++; }
                 } else {
+                    st_vol_u32(&sm.produced, k);                                    // (the 4-group path publishes it once per step only)
                     st_vol_u32(&sm.end_j, j);
                     st_vol_u32(&sm.ended, 1u);
                     mbar_arrive(&sm.full[steps & smask]); steps++;                  // closes the last (possibly empty) step
@@ -562,7 +575,12 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0,
                 {
                     const uint32_t nib = rb(pp);
                     const uint32_t n0 = nib >> 4, n1 = nib & 15u;
+#if TSQB_DEC_DESC2
+                    const uint32_t cbits = d.x >> (30u - 2u * (pi & 3u));     // a step starts at a multiple of 16 descriptors: pair pi is pair pi & 3 of its group
+                    const bool l0 = (cbits & 2u) != 0, l1 = (cbits & 1u) != 0;
+#else
                     const bool l0 = (d.x & (0x80u << 18)) != 0, l1 = (d.x & (0x40u << 18)) != 0;
+#endif
                     uint32_t dst;
                     if (half == 0) { lit = l0; len = sym_len<EXT>(n0, l0); sp = pp + 1u; dst = jp; }
                     else { lit = l1; len = sym_len<EXT>(n1, l1); sp = pp + 1u + (l0 ? n0 + 1u : 2u); dst = jp + sym_len<EXT>(n0, l0); }
@@ -810,7 +828,12 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                 const bool active = lane < np;
                 const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y;
                 const uint32_t nib = rb(pp);
+#if TSQB_DEC_DESC2
+                const uint32_t cbits = d.x >> (30u - 2u * (lane & 3u));       // a step starts at a multiple of 32 descriptors: pair L is pair L & 3 of its group
+                const bool l0 = (cbits & 2u) != 0, l1 = (cbits & 1u) != 0;
+#else
                 const bool l0 = (d.x & (0x80u << 18)) != 0, l1 = (d.x & (0x40u << 18)) != 0;
+#endif
                 uint32_t len0 = (nib >> 4) + 1u, len1 = (nib & 15u) + 1u;
                 const uint32_t sp0 = pp + 1u, sp1 = sp0 + (l0 ? len0 : 2u);
                 const uint32_t dst0 = jp, dst1 = jp + len0;

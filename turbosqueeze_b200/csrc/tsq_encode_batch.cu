@@ -196,7 +196,7 @@ __device__ __forceinline__ uint32_t wait_arrived(const uint32_t* flag, uint32_t 
         asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
         if (v >= want) return v;
         __nanosleep(500);
-        if (clock64() - t0 > 6000000000ll) { *err = 1u; return 0xFFFFFFFFu; }
+        if (clock64() - t0 > 20000000000ll) { *err = 1u; return 0xFFFFFFFFu; }   // ~10 s
     }
 }
 

@@ -77,16 +77,68 @@ def gather_bodies(body, dst=0, group=None, length=None, out=None, out_offset=0):
     return None, counts
 
 
-def gather_container(local_container, total_uncompressed, n_blocks_total, dst=0, group=None, length=None):
+def gather_bodies_peer(body, dst=0, group=None, length=None, out_offset=0):
+    """The same gather through PEER MEMORY instead of NCCL send/recv: `dst` allocates the destination, exports it as a CUDA
+    IPC handle (tsqb_ipc_export), every other rank maps it and writes its bytes straight to its prefix-summed offset with one
+    device-to-device copy over NVLink / NVSwitch (tsqb_copy_d2d); a tiny all-reduce behind the copies orders them before
+    whatever `dst` does next.  NCCL's send/recv stages through its channel buffers (~320 GB/s into the root with seven
+    senders); direct peer writes are bound by the root's NVLink ingress.  CUDA tensors + NCCL process group only.
+    Returns (destination tensor | None, counts) like gather_bodies, or None when peer memory cannot be used (all ranks agree).
+    """
+    from . import api
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = body.device
+    n = torch.tensor([body.numel()], dtype=torch.int64, device=dev) if length is None else length.reshape(1).to(torch.int64)
+    counts_t = torch.empty(world, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(counts_t, n, group=group)
+    counts = [int(c) for c in counts_t.cpu().tolist()]
+    msg = torch.zeros(80, dtype=torch.uint8, device=dev)                    # 64-byte handle | u64 offset | u64 ok
+    out = None
+    if rank == dst:
+        out = torch.empty(out_offset + sum(counts), dtype=torch.uint8, device=dev)
+        try:
+            handle, off = api.ipc_export(out.data_ptr())
+            msg.copy_(torch.frombuffer(bytearray(handle + struct.pack("<QQ", off, 1)), dtype=torch.uint8))
+        except Exception:
+            pass                                                            # ok stays 0: everybody falls back
+    dist.broadcast(msg, src=dst, group=group)
+    raw = bytes(msg.cpu().numpy())
+    off, ok = struct.unpack("<QQ", raw[64:80])
+    if not ok:
+        return None
+    at = out_offset + sum(counts[:rank])
+    base = None
+    if rank == dst:
+        out[at:at + counts[rank]].copy_(body[:counts[rank]])
+    elif counts[rank]:
+        base = api.ipc_open(raw[:64])
+        api.copy_d2d(base + off + at, body.data_ptr(), counts[rank])
+    done = torch.zeros(1, dtype=torch.int32, device=dev)
+    dist.all_reduce(done, group=group)                                      # stream-ordered behind every rank's copy
+    if base is not None:
+        torch.cuda.current_stream().synchronize()
+        api.ipc_close(base)
+    return out, counts
+
+
+def gather_container(local_container, total_uncompressed, n_blocks_total, dst=0, group=None, length=None, transport="auto"):
     """Assemble one TSQ1 container on `dst` from per-rank containers (each rank's own header is dropped).
 
     local_container: uint8 tensor holding a TSQ1 container of this rank's blocks (what Context.pack_container /
     tsqb_pack_container produce); `length`: its device-side length tensor (None = the whole tensor).
+    transport: "peer" = direct peer-memory writes (gather_bodies_peer), "nccl" = grouped send/recv (gather_bodies),
+    "auto" = peer memory for CUDA tensors under NCCL, else send/recv.
     The header is written in place in front of the gathered bodies -- no second copy of the container.
     Returns the uint8 tensor on dst, else None.
     """
     body_len = None if length is None else length.reshape(1).to(torch.int64) - HEADER
-    out, _ = gather_bodies(local_container[HEADER:], dst=dst, group=group, length=body_len, out_offset=HEADER)
+    res = None
+    if transport != "nccl" and local_container.is_cuda and dist.get_backend(group) == "nccl":
+        res = gather_bodies_peer(local_container[HEADER:], dst=dst, group=group, length=body_len, out_offset=HEADER)
+    if res is None:
+        res = gather_bodies(local_container[HEADER:], dst=dst, group=group, length=body_len, out_offset=HEADER)
+    out = res[0]
     if out is None:
         return None
     hdr = torch.frombuffer(bytearray(container_header(n_blocks_total, total_uncompressed)), dtype=torch.uint8)
@@ -94,7 +146,7 @@ def gather_container(local_container, total_uncompressed, n_blocks_total, dst=0,
     return out
 
 
-def encode_sharded(ctx, host_buf, total, block, ext=0, dst=0, group=None):
+def encode_sharded(ctx, host_buf, total, block, ext=0, dst=0, group=None, transport="auto"):
     """The N-GPU encode path: ONE input stream of `total` bytes, rank r encodes the contiguous block
     range byte_range() gives it -- its shard plus INPUT_PAD bytes of the following shard, because the last block of a
     shard reads a few bytes past itself (tsq_encode.cpp:74,126-128; zeros behind the very end) -- frames its streams
@@ -119,7 +171,7 @@ def encode_sharded(ctx, host_buf, total, block, ext=0, dst=0, group=None):
     else:                                                             # more ranks than blocks: an empty body
         cont = torch.zeros(HEADER, dtype=torch.uint8, device=dev)
         clen = torch.tensor([HEADER], dtype=torch.int64, device=dev)
-    out = gather_container(cont, total, nb_total, dst=dst, group=group, length=clen)
+    out = gather_container(cont, total, nb_total, dst=dst, group=group, length=clen, transport=transport)
     return out, {"lo": lo, "hi": hi, "hi_tail": hi_tail, "blocks": (n + block - 1) // block}
 
 
