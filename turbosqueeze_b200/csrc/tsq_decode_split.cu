@@ -21,15 +21,22 @@
 //     (cp.async.bulk + mbarrier: TMA without a tensor map; SASS UBLKCP) issued by the copier;
 //   * decoded bytes go to a shared-memory OUTPUT ring first; near matches (distance < ring) read
 //     their source there (29-cycle LDS instead of an L2 round trip), far matches read HBM/L2 bytes
-//     that an earlier step flushed;
+//     that an earlier step flushed: one aligned 128-bit load per far source (a second one only when
+//     the bytes cross its end), issued before and realigned after the step's shared-memory loads --
+//     a scattered load costs one L1TEX wavefront per lane and instruction, and that pipe is the busiest
+//     unit of this kernel (profiles/r02_experiments.md);
 //   * every symbol stores exactly its own bytes: the 16 byte stores of a lane are predicated from a
 //     length mask (ptxas turns the mask into predicates with two R2P, so this costs the same as the
 //     reference's blind 16-byte copy, tsq_decode.cpp:74-85, and needs no ordering between lanes);
 //   * symbols whose source lies inside the output of the same step are copied afterwards, in position
 //     order, lane-per-byte with their exact length (sources always precede their own pair,
-//     tsq_encode.cpp:139-141, so everything such a symbol reads is in place when it is reached);
+//     tsq_encode.cpp:139-141, so everything such a symbol reads is in place when it is reached); the
+//     lane-per-pair copier takes both symbols of a pair at once (half a warp each: they never depend
+//     on each other) with one packed shuffle per symbol;
 //   * after the step, all complete 16-byte units of the output ring are written to HBM with
 //     coalesced 128-bit stores.  Nothing is ever written past the block's decoded size.
+// A descriptor is (stream position of the pair's size byte | the group's control byte << 24, output position);
+// the copier lane picks its pair's two control bits from its own index in the step.
 #include "tsq_device.cuh"
 
 namespace tsqb {

@@ -5,8 +5,10 @@ references; the TSQ1 container is a concatenation, turbosqueeze.cpp:64-84), so t
 collective: rank r encodes / decodes its own contiguous block range.  The only exchange step is the
 assembly of ONE container from the per-rank streams (north_star: "NCCL over NVLink only to gather
 the per-GPU output streams"): an all-gather of the per-rank byte counts, then a variable-length
-gather to the destination rank at the prefix-summed offsets.  torch.distributed is the transport
-(NCCL on the GPU box, gloo in the CPU tests); tensors stay on whatever device they are on.
+gather to the destination rank at the prefix-summed offsets -- on GPUs by direct peer-memory writes
+over NVLink / NVSwitch into the destination's buffer (CUDA IPC mapping, gather_bodies_peer), with
+grouped NCCL send/recv as the fallback; gloo send/recv in the CPU tests.  torch.distributed is the
+plumbing; tensors stay on whatever device they are on.
 
 Contiguous ranges keep the reference's input over-read local: the encoder of block b reads up to 19
 bytes past the block (tsq_encode.cpp:74,126-128), i.e. into block b+1, so a rank needs its shard
