@@ -241,7 +241,7 @@ static int encode_blocks_impl(tsqb_context* c, const uint8_t* d_in, uint64_t tot
     a.fat = (c->encode_fat < 0 ? encode_wants_fat(impl, a.n_slots) : (impl == 3 && c->encode_fat != 0)) ? 1u : 0u;
     if (tables) { a.tables = tables; a.fat = impl == 3 ? 1u : 0u; }            // the pipelined path provisions sector tables
     else {
-        // The tables of all blocks in flight: up to sm_count * 32 x 4 MiB = 18.5 GiB.  On a GPU that cannot give that
+        // The tables of all blocks in flight: up to sm_count * 28 x 4 MiB = 16.2 GiB.  On a GPU that cannot give that
         // much (shared, or smaller), run with fewer blocks in flight instead of failing: halve until it fits.
         DevBuf& tb = a.fat ? c->ftables : c->tables;
         for (;;) {
@@ -513,7 +513,8 @@ static int compress_pipelined(tsqb_context* c, const uint8_t* in, uint64_t total
     int64_t slot_cap[KMAX];
     uint64_t slots_tab[KMAX], tab_at[KMAX], tab_total = 0;
     for (int k = 0; k < nchunks; k++) {
-        slot_cap[k] = c->encode_slots > 0 ? c->encode_slots : (int64_t)(((uint64_t)c->sm_count * 32 * (cb[k + 1] - cb[k]) + nb - 1) / nb);
+        const uint64_t grid_slots = impl == 3 ? encode_batch_resident_warps(c->sm_count) : (uint64_t)c->sm_count * 32;
+        slot_cap[k] = c->encode_slots > 0 ? c->encode_slots : (int64_t)((grid_slots * (cb[k + 1] - cb[k]) + nb - 1) / nb);
         slots_tab[k] = encode_slots_for(impl, cb[k + 1] - cb[k], c->sm_count, slot_cap[k]);
         tab_at[k] = tab_total; tab_total += slots_tab[k];
     }
@@ -617,7 +618,7 @@ static int compress_streamed(tsqb_context* c, const uint8_t* in, uint64_t total,
     // every block in flight: one table per block (as the chunked path provisions them, a full grid in all)
     uint64_t tab_at[KMAX], tab_total = 0;
     for (int k = 0; k < K; k++) { tab_at[k] = tab_total; tab_total += cb[k + 1] - cb[k]; }
-    if (tab_total > (uint64_t)c->sm_count * 32u) return -1;                   // more blocks than resident warps: chunked path
+    if (tab_total > encode_batch_resident_warps(c->sm_count)) return -1;      // more blocks than resident warps: chunked path
     const uint64_t ccap = 16 + per * (stride + 3) + 256;
     if (c->in.ensure(total + 2 * TSQB_INPUT_PAD) || c->slots.ensure(nb * stride + 256) || c->sizes.ensure(nb * 4 + 4) ||
         c->cont.ensure(ccap * K) || c->offs.ensure((nb + KMAX) * 8) || c->misc.ensure(64 * KMAX) || c->flags.ensure(256) ||

@@ -8,6 +8,7 @@ namespace tsqb {
 
 cudaError_t launch_encode_scalar(const EncodeArgs& a, bool ext, cudaStream_t st);
 cudaError_t launch_encode_batch(const EncodeArgs& a, bool ext, cudaStream_t st);
+uint32_t    encode_batch_resident_warps(int sm_count);
 cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cudaStream_t st, bool lane_per_pair, int slot_cap);
 #ifdef TSQB_XCHECK   // round-1 v1 kernels, kept as cross-checks in the test-only library (csrc/xcheck/)
 cudaError_t launch_encode_warp(const EncodeArgs& a, cudaStream_t st);
@@ -20,6 +21,7 @@ uint32_t encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_over
     uint64_t slots;
     if (user_override > 0) slots = (uint64_t)user_override;
     else if (impl == 1)    slots = (uint64_t)sm_count * 64u;          // threads: 2 CTAs of 32 per SM
+    else if (impl == 3)    slots = encode_batch_resident_warps(sm_count);   // every slot resident from the start (28 warps per SM)
     else                   slots = (uint64_t)sm_count * 32u;          // warps: 32 per SM
     if (slots > nb) slots = nb;
     if (slots == 0) slots = 1;

@@ -55,6 +55,8 @@ uint32_t    encode_table_bytes(int impl, bool fat);
 bool        encode_wants_fat(int impl, uint32_t n_slots);
 // how many hash tables launch_encode(impl) will use for nb blocks (caller sizes a.tables from it)
 uint32_t    encode_slots_for(int impl, uint64_t nb, int sm_count, int64_t user_override);
+// batch encoder: warps that are resident at once on the device (registers: 7 CTAs of 4 warps per SM)
+uint32_t    encode_batch_resident_warps(int sm_count);
 
 // lanes: see tsq_container.cu (34 / 35 = walker + copier kernel; 1..33 only in the cross-check library)
 cudaError_t launch_decode(const DecodeArgs& a, int lanes, bool ext, int sm_count, cudaStream_t st, int slot_cap = 0);

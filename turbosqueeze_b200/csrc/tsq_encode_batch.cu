@@ -738,6 +738,27 @@ __global__ void __launch_bounds__(kWarps * 32) encode_batch_kernel(EncodeArgs a)
 
 }  // namespace
 
+// Warps (= blocks in flight) of the batch encoder that are RESIDENT at once on this device: registers (72 per thread)
+// allow 7 CTAs of 4 warps per SM, not 8.  A launch with more slots than that runs its last CTAs as a second wave behind
+// the first one's whole block list (8 GiB of text in 256 KiB blocks: 304 ms with 148 x 32 slots), so the slot count is
+// capped here and the blocks are dealt evenly over slots that all run from the start.
+uint32_t encode_batch_resident_warps(int sm_count)
+{
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        int n = 0;
+        // the most register-hungry instantiation decides (they differ by a CTA at most)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, encode_batch_kernel<true, true, false>, kWarps * 32, 0) != cudaSuccess || n <= 0) {
+            cudaGetLastError();
+            n = 6;
+        }
+        int m = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&m, encode_batch_kernel<true, false, false>, kWarps * 32, 0) == cudaSuccess && m > 0 && m < n) n = m;
+        per_sm = n * kWarps;
+    }
+    return (uint32_t)(per_sm * sm_count);
+}
+
 cudaError_t launch_encode_batch(const EncodeArgs& a, bool ext, cudaStream_t st)
 {
     if (a.nb == 0) return cudaSuccess;
