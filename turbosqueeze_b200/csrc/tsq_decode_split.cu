@@ -67,6 +67,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_FLUSH2
 #define TSQB_DEC_FLUSH2 1          // lane-per-pair copier: flush of a step = two predicated 128-bit moves (a step leaves <= 65 units)
 #endif
+#ifndef TSQB_DEC_L2POL
+#define TSQB_DEC_L2POL 0           // L2 policies: bit 0 = far-match loads evict_first (their 64-byte fills are used once and push the freshly
+#endif                             // written output -- the next far sources -- out of the L2), bit 1 = output stores evict_last, bit 2 = far loads fill 64 B, bit 3 = stream (TMA) loads evict_first
 #ifndef TSQB_DEC_DESC2
 #define TSQB_DEC_DESC2 1           // descriptor carries the group's whole control byte (the copier lane picks its pair's two bits from its own
 #endif                             // index) and the walker publishes `produced` once per step: fewer walker instructions per pair
@@ -114,6 +117,48 @@ struct __align__(16) SlotSmem {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// 16 bytes of already flushed output (a far match source): around L1, optionally marked evict_first in L2
+__device__ __forceinline__ uint4 ld_far16(const uint4* g)
+{
+#if TSQB_DEC_L2POL & 1
+    uint4 v;
+    const uint64_t pol = l2_policy_evict_first();
+#if TSQB_DEC_L2POL & 4
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g), "l"(pol) : "memory");
+#else
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(g), "l"(pol) : "memory");
+#endif
+    return v;
+#else
+    return __ldcg(g);
+#endif
+}
+
+// 16 bytes of decoded output to HBM (a later far match may read them back): optionally marked evict_last in L2
+__device__ __forceinline__ void st_out16(uint8_t* p, const uint4& x)
+{
+#if TSQB_DEC_L2POL & 2
+    const uint64_t pol = l2_policy_evict_last();
+    asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(x.x), "r"(x.y), "r"(x.z), "r"(x.w), "l"(pol) : "memory");
+#else
+    *reinterpret_cast<uint4*>(p) = x;
+#endif
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -157,8 +202,16 @@ __device__ __forceinline__ void mbar_wait_addr(uint32_t bar_addr, uint32_t parit
 // 1-D bulk async copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
 {
+#if TSQB_DEC_L2POL & 8
+    // the compressed stream is read exactly once: do not let it displace the output the far matches read back
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+#endif
 }
 
 __device__ __forceinline__ uint32_t ld_vol_u32(const uint32_t* p)
@@ -398,9 +451,9 @@ __device__ __forceinline__ void far_issue(const uint8_t* src, uint32_t len, uint
 {
     const uintptr_t ad = reinterpret_cast<uintptr_t>(src);
     const uint4* g = reinterpret_cast<const uint4*>(ad & ~(uintptr_t)15);
-    A = __ldcg(g);
+    A = ld_far16(g);
     B = make_uint4(0, 0, 0, 0);
-    if ((uint32_t)(ad & 15u) + len > 16u) B = __ldcg(g + 1);
+    if ((uint32_t)(ad & 15u) + len > 16u) B = ld_far16(g + 1);
 }
 
 __device__ __forceinline__ void far_words(const uint8_t* src, const uint4& A, const uint4& B, uint32_t w[5])
@@ -531,13 +584,13 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0,
                 if (at < E) {
                     uint4 x;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
-                    *reinterpret_cast<uint4*>(o_al + at) = x;
+                    st_out16(o_al + at, x);
                 }
             }
             for (uint32_t at = F + 16u * lane + 1024u; at < E; at += 512u) {     // never taken for regular steps
                 uint4 x;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
-                *reinterpret_cast<uint4*>(o_al + at) = x;
+                st_out16(o_al + at, x);
             }
             F = E;
         };
@@ -764,7 +817,7 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
                 if (at < E) {
                     uint4 x;
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
-                    *reinterpret_cast<uint4*>(o_al + at) = x;
+                    st_out16(o_al + at, x);
                 }
             }
             if (F + 1024u < E)
@@ -772,7 +825,7 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
             for (uint32_t at = F + 16u * lane + (TSQB_DEC_FLUSH2 ? 1024u : 0u); at < E; at += 512u) {
                 uint4 x;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(obase + (at & kOMask)));
-                *reinterpret_cast<uint4*>(o_al + at) = x;
+                st_out16(o_al + at, x);
             }
             F = E;
         };
