@@ -198,7 +198,8 @@ void tsqDecode(uint8_t* inputBlock, uint8_t* outputBlock, uint32_t* outputSize, 
 /* Block size used by tsqCompress / tsqCompress_MT / tsqCompressAsync_MT (process-wide; default 4 MiB = the
  * reference's TSQ_BLOCK_SZ, which makes the containers byte-identical to the reference's).  The container does not
  * record the block size and the reference decodes any block <= 4 MiB, so e.g. 256 KiB keeps the files readable by
- * the reference while giving the GPU 16x more independent blocks.  Returns 0 on success. */
+ * the reference while giving the GPU 16x more independent blocks.  Returns 0 on success.  The environment variable
+ * TSQB_CONTAINER_BLOCK=<bytes>, read when the library is loaded, sets the same default. */
 int tsqb_set_container_block_size(uint32_t block_size);
 
 /* turbosqueeze.h:458,470 -- TSQ1 files, 4 MiB blocks by default; `level` is ignored as in the reference

@@ -955,7 +955,18 @@ extern "C" int tsqb_decompress_into(tsqb_context* c, const uint8_t* in, uint64_t
 // reference cuts 4 MiB blocks (turbosqueeze.h:37-38) and so does the default here, which makes the containers
 // identical; the container does not record the block size and the reference's decoder accepts any block <= 4 MiB
 // (tsq_decode.cpp:53), so a smaller block stays readable by `tsq d` while giving the GPU 16x more blocks in flight.
-static std::atomic<uint32_t> g_container_block{kBlockMax};
+static uint32_t container_block_default()
+{
+    // TSQB_CONTAINER_BLOCK=<bytes>: the same switch as tsqb_set_container_block_size for a caller that cannot be recompiled
+    const char* e = getenv("TSQB_CONTAINER_BLOCK");
+    if (e && *e) {
+        const unsigned long v = strtoul(e, nullptr, 0);
+        if (v >= 1 && v <= kBlockMax) return (uint32_t)v;
+        fprintf(stderr, "turbosqueeze_b200: TSQB_CONTAINER_BLOCK=%s ignored (not in 1..%u)\n", e, kBlockMax);
+    }
+    return kBlockMax;
+}
+static std::atomic<uint32_t> g_container_block{container_block_default()};
 
 extern "C" int tsqb_set_container_block_size(uint32_t block_size)
 {
