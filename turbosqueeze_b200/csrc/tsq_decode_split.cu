@@ -117,6 +117,7 @@ struct __align__(16) SlotSmem {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+#if TSQB_DEC_L2POL
 __device__ __forceinline__ uint64_t l2_policy_evict_first()
 {
     uint64_t p;
@@ -130,6 +131,7 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+#endif
 
 // 16 bytes of already flushed output (a far match source): around L1, optionally marked evict_first in L2
 __device__ __forceinline__ uint4 ld_far16(const uint4* g)
