@@ -67,6 +67,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_FLUSH2
 #define TSQB_DEC_FLUSH2 1          // lane-per-pair copier: flush of a step = two predicated 128-bit moves (a step leaves <= 65 units)
 #endif
+#ifndef TSQB_DEC_LIT16
+#define TSQB_DEC_LIT16 1           // incompressible data: the walker checks a group of eight 16-byte literals with four independent loads
+#endif                             // (its layout is fixed), and the lane-per-symbol copier stores aligned 16-byte symbols with one 128-bit store
 #ifndef TSQB_DEC_L2POL
 #define TSQB_DEC_L2POL 0           // L2 policies: bit 0 = far-match loads evict_first (their 64-byte fills are used once and push the freshly
 #endif                             // written output -- the next far sources -- out of the L2), bit 1 = output stores evict_last, bit 2 = far loads fill 64 B, bit 3 = stream (TMA) loads evict_first
@@ -328,6 +331,22 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                         const uint32_t c = lds_u8(pr);
                         uint32_t prp = pr + 1u;
                         const uint32_t c24 = c << 24;
+#if TSQB_DEC_LIT16 && TSQB_DEC_DESC2
+                        // Eight 16-byte literals (control byte 0xFF, four size bytes 0xFF: what incompressible data encodes to,
+                        // tsq_encode.cpp:85-97) are a group of fixed layout -- size bytes 33 bytes apart -- so they are verified with
+                        // four independent loads instead of the chain load -> lengths -> next load.
+                        bool lit16 = false;
+                        if (c == 0xFFu) {
+                            const uint32_t a0 = lds_u8(prp), a1 = lds_u8(prp + 33u), a2 = lds_u8(prp + 66u), a3 = lds_u8(prp + 99u);
+                            lit16 = (a0 & a1 & a2 & a3) == 0xFFu;
+                        }
+                        if (lit16) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) put_desc(dsl + 8u * q, (prp + 33u * q + dlt) | c24, j + 32u * q);
+                            prp += 132u;
+                            j += 128u;
+                        } else
+#endif
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t nib = lds_u8(prp);
@@ -691,6 +710,12 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0,
                     }
                     placed = now;
                 }
+#if TSQB_DEC_LIT16
+                // every symbol of the step a full, 16-byte aligned run (a block of 16-byte literals): one 128-bit store each
+                if (__all_sync(FULL, !placed || (len == 16u && (q & 15u) == 0u))) {
+                    if (placed) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(obase + (q & kOMask)), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+                } else
+#endif
                 if (placed) store16(obase, kOMask, q, v, (q & kOMask) + 16u > OUT_RING, (1u << min(len, 16u)) - 1u);
                 // ---- symbols whose source lies inside this step's output: in position order, one at a time, the
                 // warp copying a symbol's bytes lane-per-byte.  Sources always precede their own pair (tsq_encode.cpp:139-141), so by
