@@ -44,9 +44,12 @@ namespace tsqb {
 namespace {
 
 constexpr unsigned FULL      = 0xffffffffu;
-constexpr uint32_t kChunk    = 512;                  // bytes per bulk copy
-constexpr uint32_t kChunks   = 8;                    // ring slots
-constexpr uint32_t kInRing   = kChunk * kChunks;     // 4 KiB of stream per block slot
+#ifndef TSQB_DEC_CHUNK
+#define TSQB_DEC_CHUNK 512         // bytes per bulk copy of the stream (the 4 KiB ring holds 4096 / TSQB_DEC_CHUNK of them)
+#endif
+constexpr uint32_t kChunk    = TSQB_DEC_CHUNK;       // bytes per bulk copy
+constexpr uint32_t kInRing   = 4096;                 // 4 KiB of stream per block slot
+constexpr uint32_t kChunks   = kInRing / kChunk;     // ring slots
 constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_BULK4
 #define TSQB_DEC_BULK4 1           // development knob: walker takes 4 groups per limit test when far from every limit
@@ -70,6 +73,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_LIT16
 #define TSQB_DEC_LIT16 1           // incompressible data: the walker checks a group of eight 16-byte literals with four independent loads
 #endif                             // (its layout is fixed), and the lane-per-symbol copier stores aligned 16-byte symbols with one 128-bit store
+#ifndef TSQB_DEC_DENSE_PAIRS
+#define TSQB_DEC_DENSE_PAIRS 0     // 1: (nearly) incompressible blocks take the lane-per-pair copier too (random 1 GB: 1.19 vs 0.96 ms: worse)
+#endif
 #ifndef TSQB_DEC_L2POL
 #define TSQB_DEC_L2POL 0           // L2 policies: bit 0 = far-match loads evict_first (their 64-byte fills are used once and push the freshly
 #endif                             // written output -- the next far sources -- out of the L2), bit 1 = output stores evict_last, bit 2 = far loads fill 64 B, bit 3 = stream (TMA) loads evict_first
@@ -985,8 +991,17 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
 #pragma unroll
                     for (int m = 0; m < 4; m++) v1[m] = __funnelshift_r(w1[m], w1[m + 1], sh);
                 }
+#if TSQB_DEC_LIT16 && TSQB_DEC_DENSE_PAIRS
+                // every symbol of the step a full, 16-byte aligned run (16-byte literals): one 128-bit store each
+                if (__all_sync(FULL, (!now0 || (len0 == 16u && (q0 & 15u) == 0u)) && (!now1 || (len1 == 16u && (q1 & 15u) == 0u)))) {
+                    if (now0) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(obase + (q0 & kOMask)), "r"(v0[0]), "r"(v0[1]), "r"(v0[2]), "r"(v0[3]) : "memory");
+                    if (now1) asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(obase + (q1 & kOMask)), "r"(v1[0]), "r"(v1[1]), "r"(v1[2]), "r"(v1[3]) : "memory");
+                } else
+#endif
+                {
                 if (now0) store16(obase, kOMask, q0, v0, (q0 & kOMask) + 16u > OUT_RING, (1u << len0) - 1u);
                 if (now1) store16(obase, kOMask, q1, v1, (q1 & kOMask) + 16u > OUT_RING, (1u << len1) - 1u);
+                }
 
                 // ---- symbols whose source lies inside this step's output: in position order, pair by pair; sources always
                 // precede their own pair (tsq_encode.cpp:139-141), so the two symbols of a pair never depend on each other
@@ -1080,7 +1095,7 @@ __global__ void __launch_bounds__(LB, 1) decode_split_kernel(DecodeArgs a, uint3
                 // ... and unless it is almost all 16-byte matches (C/U < 0.3): periodic data, where every match copies from
                 // inside its own step and the in-order copies dominate (8-byte period: 6.5 vs 8.3 ms per 2 GiB)
                 const bool runs = (uint64_t)limit * 10u < a.ostride * 3u;
-                if (dense || runs) copier<OUT_RING, EXT, true>(a, slots[wid], b, stride_slots, lane, cs);
+                if ((dense && !TSQB_DEC_DENSE_PAIRS) || runs) copier<OUT_RING, EXT, true>(a, slots[wid], b, stride_slots, lane, cs);
                 else       copier_pairs<OUT_RING>(a, slots[wid], b, lane, cs);
             }
         } else copier<OUT_RING, EXT, false>(a, slots[wid], b0, stride_slots, lane, cs);
