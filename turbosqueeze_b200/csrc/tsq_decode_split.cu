@@ -76,6 +76,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #ifndef TSQB_DEC_DENSE_PAIRS
 #define TSQB_DEC_DENSE_PAIRS 0     // 1: (nearly) incompressible blocks take the lane-per-pair copier too (random 1 GB: 1.19 vs 0.96 ms: worse)
 #endif
+#ifndef TSQB_DEC_EAGER
+#define TSQB_DEC_EAGER 1           // walker notes a landed stream chunk as soon as it comes within the 4-group path's look-ahead of the
+#endif                             // landed frontier (0: only within one pair's look-ahead -- which keeps it off the 4-group path for good)
 #ifndef TSQB_DEC_L2POL
 #define TSQB_DEC_L2POL 0           // L2 policies: bit 0 = far-match loads evict_first (their 64-byte fills are used once and push the freshly
 #endif                             // written output -- the next far sources -- out of the L2), bit 1 = output stores evict_last, bit 2 = far loads fill 64 B, bit 3 = stream (TMA) loads evict_first
@@ -86,7 +89,8 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #define TSQB_DEC_DIAG 0            // timing diagnostic, WRONG OUTPUT: 1 = the lane-per-pair copier moves no bytes (walker + hand-over + flush only)
 #endif
 #ifndef TSQB_DEC_WMASK
-#define TSQB_DEC_WMASK 0           // walker: 1 = the 4-group path masks its ring addresses instead of requiring that it does not wrap (2.615 vs 2.600 ms: no gain)
+#define TSQB_DEC_WMASK 1           // walker: the 4-group path masks its ring addresses instead of requiring that it does not wrap (with TSQB_DEC_EAGER:
+                                   // 2.600 -> 2.560 ms; without the mask the lanes of a walker warp split over two paths: 2.909 ms)
 #endif
 constexpr uint32_t kQueue    = TSQB_DEC_QUEUE;       // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
@@ -295,7 +299,8 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
         for (int rep = 0; rep < 8; rep++) {
             if (phase == P_WALK) {
                 // take note of freshly landed chunks before deciding how far this lane may go
-                if (avail != nchunks && p + 4u * kLook > avail * kChunk) {
+                // (the 4-group path below needs 4 * 133 + 4 * kLook landed bytes ahead of p: look for the next chunk that early)
+                if (avail != nchunks && p + (TSQB_DEC_EAGER ? 4u * 133u + 4u * kLook : 4u * kLook) > avail * kChunk) {
                     const uint32_t s = avail % kChunks;
                     if (mbar_test(&sm.bar[s], (bits >> s) & 1u)) { bits ^= 1u << s; avail++; }
                 }
@@ -348,7 +353,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                         }
                         if (lit16) {
 #pragma unroll
-                            for (int q = 0; q < 4; q++) put_desc(dsl + 8u * q, (prp + 33u * q + dlt) | c24, j + 32u * q);
+                            for (int q = 0; q < 4; q++) put_desc(dsl + 8u * q, (prp + 33u * q + dlt) | c24, (j + 32u * q) | 0x80000000u);   // bit 31: a verified (L16, L16) pair
                             prp += 132u;
                             j += 128u;
                         } else
@@ -654,11 +659,36 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0,
                 const uint32_t plast = __shfl_sync(FULL, d.x & 0xFFFFFFu, (np - 1u) * 2u);
                 if ((plast + kLook - 2u) / kChunk >= waited) wait_upto((plast + kLook - 2u) / kChunk + 1u);
 
+#if TSQB_DEC_LIT16 && TSQB_DEC_DESC2
+                if constexpr (!EXT) {
+                    // ---- a step of sixteen pairs the walker has verified as two 16-byte literals each (incompressible data):
+                    // symbol L is 16 bytes at stream position pp + 1 + 16 * (L & 1) and output byte 16 * L of the step.  When the
+                    // step starts on a 16-byte unit of HBM with everything before it flushed, the bytes go to the ring (a later
+                    // near match may read them) AND straight to HBM: no lengths, no classification, no separate flush.
+                    const uint32_t Jd = (__shfl_sync(FULL, d.y, 0) & 0x7FFFFFFFu) + oal;
+                    if (np == kPairs && __all_sync(FULL, (d.y >> 31) != 0u) && F == Jd && (Jd & 15u) == 0u) {
+                        const uint32_t spd = (d.x & 0xFFFFFFu) + 1u + 16u * half;
+                        const uint32_t qd = Jd + 16u * lane;
+                        uint32_t vd[4];
+                        const bool wrapd = __any_sync(FULL, (spd & kInMask) + 20u > kInRing);
+                        load16_smem(ibase, kInMask, spd, vd, wrapd);
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(obase + (qd & kOMask)), "r"(vd[0]), "r"(vd[1]), "r"(vd[2]), "r"(vd[3]) : "memory");
+                        st_out16(o_al + qd, make_uint4(vd[0], vd[1], vd[2], vd[3]));
+                        __syncwarp();
+                        F = Jd + 512u;
+                        kc += np;
+                        const uint32_t c0d = __shfl_sync(FULL, d.x & 0xFFFFFFu, 0) / kChunk;
+                        if (c0d != cur_chunk) { cur_chunk = c0d; issue_upto(c0d + kChunks); }
+                        if (lane == 0) st_vol_u32(&sm.consumed, kc);
+                        continue;                                                 // a full step: the block goes on
+                    }
+                }
+#endif
                 // ---- one lane per symbol
                 bool active = pi < np;
                 uint32_t len = 0, q = 0, sp = 0, srcq = 0;
                 bool lit = true;
-                const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y;
+                const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y & 0x7FFFFFFFu;          // (bit 31 of d.y: the walker's (L16, L16) flag)
                 {
                     const uint32_t nib = rb(pp);
                     const uint32_t n0 = nib >> 4, n1 = nib & 15u;
@@ -919,7 +949,7 @@ __device__ void copier_pairs(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64
 
                 // ---- lane L: both symbols of pair L (tsq_decode.cpp:68-86)
                 const bool active = lane < np;
-                const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y;
+                const uint32_t pp = d.x & 0xFFFFFFu, jp = d.y & 0x7FFFFFFFu;          // (bit 31 of d.y: the walker's (L16, L16) flag)
                 const uint32_t nib = rb(pp);
 #if TSQB_DEC_DESC2
                 const uint32_t cbits = d.x >> (30u - 2u * (lane & 3u));       // a step starts at a multiple of 32 descriptors: pair L is pair L & 3 of its group
