@@ -77,7 +77,7 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #define TSQB_DEC_DENSE_PAIRS 0     // 1: (nearly) incompressible blocks take the lane-per-pair copier too (random 1 GB: 1.19 vs 0.96 ms: worse)
 #endif
 #ifndef TSQB_DEC_EAGER
-#define TSQB_DEC_EAGER 1           // walker notes a landed stream chunk as soon as it comes within the 4-group path's look-ahead of the
+#define TSQB_DEC_EAGER 2           // walker notes a landed stream chunk as soon as it comes within the 4-group path's look-ahead of the
 #endif                             // landed frontier (0: only within one pair's look-ahead -- which keeps it off the 4-group path for good)
 #ifndef TSQB_DEC_L2POL
 #define TSQB_DEC_L2POL 0           // L2 policies: bit 0 = far-match loads evict_first (their 64-byte fills are used once and push the freshly
@@ -300,6 +300,12 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
             if (phase == P_WALK) {
                 // take note of freshly landed chunks before deciding how far this lane may go
                 // (the 4-group path below needs 4 * 133 + 4 * kLook landed bytes ahead of p: look for the next chunk that early)
+#if TSQB_DEC_EAGER >= 2
+                // (two chunks per iteration: one iteration of the 4-group path can consume more than a whole chunk of dense data, so
+                // noting one chunk per iteration would leave the walk within a chunk of the frontier it knows of for good)
+#pragma unroll
+                for (int t = 0; t < 2; t++)
+#endif
                 if (avail != nchunks && p + (TSQB_DEC_EAGER ? 4u * 133u + 4u * kLook : 4u * kLook) > avail * kChunk) {
                     const uint32_t s = avail % kChunks;
                     if (mbar_test(&sm.bar[s], (bits >> s) & 1u)) { bits ^= 1u << s; avail++; }
@@ -390,6 +396,16 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     const uint32_t dsl = dbase + ((k & kQMask) << 3);
                     const uint32_t c = ring_u8(p);                                  // :62
                     uint32_t pp = p + 1u;
+#if TSQB_DEC_LIT16 && TSQB_DEC_DESC2
+                    bool lit16 = false;                                             // eight 16-byte literals: see the 4-group path
+                    if (!EXT && c == 0xFFu) lit16 = (ring_u8(pp) & ring_u8(pp + 33u) & ring_u8(pp + 66u) & ring_u8(pp + 99u)) == 0xFFu;
+                    if (lit16) {
+#pragma unroll
+                        for (int q = 0; q < 4; q++) put_desc(dsl + 8u * q, (pp + 33u * q) | (c << 24), (j + 32u * q) | 0x80000000u);
+                        pp += 132u;
+                        j += 128u;
+                    } else
+#endif
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const uint32_t nib = ring_u8(pp);                           // :68
