@@ -678,20 +678,52 @@ __device__ void copier(const DecodeArgs& a, SlotSmem<OUT_RING>& sm, uint64_t b0,
 #if TSQB_DEC_LIT16 && TSQB_DEC_DESC2
                 if constexpr (!EXT) {
                     // ---- a step of sixteen pairs the walker has verified as two 16-byte literals each (incompressible data):
-                    // symbol L is 16 bytes at stream position pp + 1 + 16 * (L & 1) and output byte 16 * L of the step.  When the
-                    // step starts on a 16-byte unit of HBM with everything before it flushed, the bytes go to the ring (a later
-                    // near match may read them) AND straight to HBM: no lengths, no classification, no separate flush.
+                    // symbol L is 16 bytes at stream position pp + 1 + 16 * (L & 1) and output byte 16 * L of the step: no lengths,
+                    // no classification.  The 512 bytes go to the output ring (a later near match may read them) as aligned words:
+                    // lane L owns words 4L .. 4L + 3 of the step's 4-byte aligned image, realigned from its own symbol and the last
+                    // word of lane L - 1 by the step's (warp-uniform) byte offset -- an accidental match early in a block shifts every
+                    // later literal off its 16-byte unit.  When the step starts on a 16-byte unit with everything before it flushed
+                    // the bytes also go straight to HBM; otherwise the usual ring -> HBM flush follows.
                     const uint32_t Jd = (__shfl_sync(FULL, d.y, 0) & 0x7FFFFFFFu) + oal;
-                    if (np == kPairs && __all_sync(FULL, (d.y >> 31) != 0u) && F == Jd && (Jd & 15u) == 0u) {
+                    if (np == kPairs && __all_sync(FULL, (d.y >> 31) != 0u)) {
                         const uint32_t spd = (d.x & 0xFFFFFFu) + 1u + 16u * half;
-                        const uint32_t qd = Jd + 16u * lane;
                         uint32_t vd[4];
                         const bool wrapd = __any_sync(FULL, (spd & kInMask) + 20u > kInRing);
                         load16_smem(ibase, kInMask, spd, vd, wrapd);
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(obase + (qd & kOMask)), "r"(vd[0]), "r"(vd[1]), "r"(vd[2]), "r"(vd[3]) : "memory");
-                        st_out16(o_al + qd, make_uint4(vd[0], vd[1], vd[2], vd[3]));
+                        const uint32_t sb = Jd & 3u;                              // warp-uniform
+                        if ((Jd & 15u) == 0u) {
+                            const uint32_t qd = Jd + 16u * lane;
+                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(obase + (qd & kOMask)), "r"(vd[0]), "r"(vd[1]), "r"(vd[2]), "r"(vd[3]) : "memory");
+                            if (F == Jd) { st_out16(o_al + qd, make_uint4(vd[0], vd[1], vd[2], vd[3])); F = Jd + 512u; }
+                        } else {
+                            const uint32_t prev3 = __shfl_up_sync(FULL, vd[3], 1);
+                            const uint32_t s8 = sb * 8u;
+                            uint32_t wd[4];
+                            wd[0] = __funnelshift_l(prev3, vd[0], s8);            // (sb == 0: the words as they are)
+                            wd[1] = __funnelshift_l(vd[0], vd[1], s8);
+                            wd[2] = __funnelshift_l(vd[1], vd[2], s8);
+                            wd[3] = __funnelshift_l(vd[2], vd[3], s8);
+                            const uint32_t w0 = Jd - sb + 16u * lane;             // q of this lane's first aligned word
+                            if (lane == 0 && sb) {
+                                // the first word also holds sb bytes of the symbol before this step: store only this step's bytes
+                                for (uint32_t t = sb; t < 4u; t++)
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(obase + ((w0 + t) & kOMask)), "r"(vd[0] >> (8u * (t - sb))) : "memory");
+                            } else
+                                asm volatile("st.shared.u32 [%0], %1;" ::"r"(obase + (w0 & kOMask)), "r"(wd[0]) : "memory");
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(obase + ((w0 + 4u) & kOMask)), "r"(wd[1]) : "memory");
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(obase + ((w0 + 8u) & kOMask)), "r"(wd[2]) : "memory");
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(obase + ((w0 + 12u) & kOMask)), "r"(wd[3]) : "memory");
+                            if (lane == 31 && sb) {
+                                // ... and the step's last sb bytes sit in a word of their own
+                                for (uint32_t t = 0; t < sb; t++)
+                                    asm volatile("st.shared.u8 [%0], %1;" ::"r"(obase + ((w0 + 16u + t) & kOMask)), "r"(vd[3] >> (8u * (4u - sb + t))) : "memory");
+                            }
+                        }
                         __syncwarp();
-                        F = Jd + 512u;
+                        if (F != Jd + 512u) {                                     // not stored directly: the usual flush of complete units
+                            const uint32_t J1d = Jd + 512u;
+                            if (F & 15u) flush(J1d, false); else if ((J1d & ~15u) > F) flush_units(J1d & ~15u);
+                        }
                         kc += np;
                         const uint32_t c0d = __shfl_sync(FULL, d.x & 0xFFFFFFu, 0) / kChunk;
                         if (c0d != cur_chunk) { cur_chunk = c0d; issue_upto(c0d + kChunks); }
