@@ -77,8 +77,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #define TSQB_DEC_DENSE_PAIRS 0     // 1: (nearly) incompressible blocks take the lane-per-pair copier too (random 1 GB: 1.19 vs 0.96 ms: worse)
 #endif
 #ifndef TSQB_DEC_EAGER
-#define TSQB_DEC_EAGER 2           // walker notes a landed stream chunk as soon as it comes within the 4-group path's look-ahead of the
-#endif                             // landed frontier (0: only within one pair's look-ahead -- which keeps it off the 4-group path for good)
+#define TSQB_DEC_EAGER 1           // walker notes a landed stream chunk as soon as it comes within the 4-group path's look-ahead of the
+#endif                             // landed frontier (0: only within one pair's look-ahead -- which keeps it off the 4-group path for good;
+                                   // 2: two chunks per iteration -- no faster once the one-group path has the literal shortcut, and small blocks lose)
 #ifndef TSQB_DEC_L2POL
 #define TSQB_DEC_L2POL 0           // L2 policies: bit 0 = far-match loads evict_first (their 64-byte fills are used once and push the freshly
 #endif                             // written output -- the next far sources -- out of the L2), bit 1 = output stores evict_last, bit 2 = far loads fill 64 B, bit 3 = stream (TMA) loads evict_first
