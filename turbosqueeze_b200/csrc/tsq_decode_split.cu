@@ -269,9 +269,16 @@ __device__ __forceinline__ const uint8_t* stream_of(const DecodeArgs& a, uint64_
 // Lane L walks the token stream of slot L.  All lanes run the same loop; a lane that has to wait
 // (stream chunk not landed, descriptor queue full, copier still setting the block up) simply does
 // nothing in that iteration.
-template <uint32_t OUT_RING, bool EXT>
+// LEAN: the flavour for batches of small blocks (< 64 KiB: the 30-slot launch), whose walks are mostly start-up -- no early
+// chunk polling, no masked 4-group path, no literal-group check (8 GiB of text in 16 KiB blocks: 28.0 -> 23.4 ms without them).
+template <uint32_t OUT_RING, bool EXT, bool LEAN>
 __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t nslots, uint32_t widx, unsigned lane)
 {
+    constexpr bool kEager = TSQB_DEC_EAGER && !LEAN, kWMask = TSQB_DEC_WMASK && !LEAN;
+    constexpr bool kLit16 = TSQB_DEC_LIT16 && TSQB_DEC_DESC2 && !LEAN && !EXT;
+    // LEAN: how close to the landed frontier the walk comes before it looks for the next chunk.  Blocks of <= 8 KiB (a stream of a
+    // few chunks) gain from looking early (1 GB in 4 KiB blocks: 3.53 -> 3.23 ms), 16 KiB blocks lose (2.70 -> 2.91 ms).
+    const uint32_t lean_need = (LEAN && TSQB_DEC_EAGER && a.ostride <= 8192u) ? 4u * 133u + 4u * kLook : 4u * kLook;
     uint32_t pmask = kPairs - 1u, smask = kQueue / kPairs - 1u;   // per block: descriptors per step - 1, step barriers in use - 1
     enum { P_DONE = 0, P_WAIT = 1, P_WALK = 2 };
     const uint64_t stride_slots = (uint64_t)gridDim.x * nslots;
@@ -307,7 +314,7 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
 #pragma unroll
                 for (int t = 0; t < 2; t++)
 #endif
-                if (avail != nchunks && p + (TSQB_DEC_EAGER ? 4u * 133u + 4u * kLook : 4u * kLook) > avail * kChunk) {
+                if (avail != nchunks && p + (kEager ? 4u * 133u + 4u * kLook : lean_need) > avail * kChunk) {
                     const uint32_t s = avail % kChunks;
                     if (mbar_test(&sm.bar[s], (bits >> s) & 1u)) { bits ^= 1u << s; avail++; }
                 }
@@ -331,30 +338,28 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                 // every limit -- and of the end of the stream ring, so that the walk can use a plain shared-memory pointer: the
                 // per-group tests and the ring wrap (mask + base) drop out of the serial chain (load, 3 ALU, load).
                 if ((k & 3u) == 0 && p + 4u * 133u + 4u * kLook <= p_safe && (k - cons) + 16u <= kQueue && j + 4u * 128u + (EXT ? 512u : 128u) < size && !EXT &&
-                    (TSQB_DEC_WMASK || (p & kInMask) + 4u * 133u + 8u <= kInRing)) {
-#if TSQB_DEC_WMASK
-                    // ring addresses are masked (one LOP3 on the chain) so that a lane near the end of its ring stays on
-                    // this path: lanes of one warp that sit on different paths execute them one after the other
-                    uint32_t pr = p;
-                    const uint32_t dlt = 0;
-                    auto lds_u8 = [&](uint32_t pos) -> uint32_t { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(rbase + (pos & kInMask))); return v; };
-#else
-                    uint32_t pr = rbase + (p & kInMask);          // shared address of stream position p
-                    const uint32_t dlt = p - pr;                  // stream position = shared address + dlt
-                    auto lds_u8 = [](uint32_t ad) -> uint32_t { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(ad)); return v; };
-#endif
+                    (kWMask || (p & kInMask) + 4u * 133u + 8u <= kInRing)) {
+                    // kWMask: ring addresses are masked (one LOP3 on the chain) so that a lane near the end of its ring stays on
+                    // this path: lanes of one warp that sit on different paths execute them one after the other.  Else the walk
+                    // uses a plain shared-memory pointer (stream position = shared address + dlt).
+                    uint32_t pr = kWMask ? p : rbase + (p & kInMask);
+                    const uint32_t dlt = kWMask ? 0u : p - pr;
+                    auto lds_u8 = [&](uint32_t pos) -> uint32_t {
+                        uint32_t v;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(kWMask ? rbase + (pos & kInMask) : pos));
+                        return v;
+                    };
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         const uint32_t dsl = dbase + ((k & kQMask) << 3);
                         const uint32_t c = lds_u8(pr);
                         uint32_t prp = pr + 1u;
                         const uint32_t c24 = c << 24;
-#if TSQB_DEC_LIT16 && TSQB_DEC_DESC2
                         // Eight 16-byte literals (control byte 0xFF, four size bytes 0xFF: what incompressible data encodes to,
                         // tsq_encode.cpp:85-97) are a group of fixed layout -- size bytes 33 bytes apart -- so they are verified with
                         // four independent loads instead of the chain load -> lengths -> next load.
                         bool lit16 = false;
-                        if (c == 0xFFu) {
+                        if (kLit16 && c == 0xFFu) {
                             const uint32_t a0 = lds_u8(prp), a1 = lds_u8(prp + 33u), a2 = lds_u8(prp + 66u), a3 = lds_u8(prp + 99u);
                             lit16 = (a0 & a1 & a2 & a3) == 0xFFu;
                         }
@@ -364,7 +369,6 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                             prp += 132u;
                             j += 128u;
                         } else
-#endif
 #pragma unroll
                         for (int q = 0; q < 4; q++) {
                             const uint32_t nib = lds_u8(prp);
@@ -397,16 +401,14 @@ __device__ void walker(const DecodeArgs& a, SlotSmem<OUT_RING>* slots, uint32_t 
                     const uint32_t dsl = dbase + ((k & kQMask) << 3);
                     const uint32_t c = ring_u8(p);                                  // :62
                     uint32_t pp = p + 1u;
-#if TSQB_DEC_LIT16 && TSQB_DEC_DESC2
                     bool lit16 = false;                                             // eight 16-byte literals: see the 4-group path
-                    if (!EXT && c == 0xFFu) lit16 = (ring_u8(pp) & ring_u8(pp + 33u) & ring_u8(pp + 66u) & ring_u8(pp + 99u)) == 0xFFu;
+                    if (kLit16 && c == 0xFFu) lit16 = (ring_u8(pp) & ring_u8(pp + 33u) & ring_u8(pp + 66u) & ring_u8(pp + 99u)) == 0xFFu;
                     if (lit16) {
 #pragma unroll
                         for (int q = 0; q < 4; q++) put_desc(dsl + 8u * q, (pp + 33u * q) | (c << 24), (j + 32u * q) | 0x80000000u);
                         pp += 132u;
                         j += 128u;
                     } else
-#endif
 #pragma unroll
                     for (int q = 0; q < 4; q++) {
                         const uint32_t nib = ring_u8(pp);                           // :68
@@ -1178,7 +1180,7 @@ __global__ void __launch_bounds__(LB, 1) decode_split_kernel(DecodeArgs a, uint3
                 else       copier_pairs<OUT_RING>(a, slots[wid], b, lane, cs);
             }
         } else copier<OUT_RING, EXT, false>(a, slots[wid], b0, stride_slots, lane, cs);
-    } else walker<OUT_RING, EXT>(a, slots, nslots, wid - nslots, lane);
+    } else walker<OUT_RING, EXT, (LB == 1024 && PAIRS == 32)>(a, slots, nslots, wid - nslots, lane);
 }
 
 template <uint32_t OUT_RING, bool EXT, uint32_t PAIRS = kPairs, int LB = TSQB_DEC_LB>
