@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
 #include <vector>
 
 static std::vector<uint8_t> make_text(size_t n, uint32_t seed)
@@ -120,6 +121,64 @@ int main()
         tsqDeallocateContextDecompression_MT(d);
         for (int j = 0; j < J; j++) { free(blob[j]); free(back[j]); }
         for (int j = 0; j < 4; j++) free(b2[j]);
+    }
+    // ---- the callback contract of the reference's writer thread (tsq_threads.cpp:248-268, :654-668): one progress call per
+    // block with (blocks written) / n_blocks, in order, then the completion call; jobs of one context deliver their callbacks
+    // in submission order even when two of them run on the GPU at once
+    {
+        TSQCompressionContext_MT* c = tsqAllocateContextCompression_MT(false);
+        TSQDecompressionContext_MT* d = tsqAllocateContextDecompression_MT(false);
+        const int J = 6;
+        const size_t n_blocks = (N + (4u << 20) - 1) / (4u << 20);                 // 4 MiB blocks (TSQ_BLOCK_SZ): 3 for this input
+        std::vector<uint8_t*> blob(J, nullptr);
+        std::vector<size_t> bn(J, 0);
+        std::mutex m;
+        std::vector<std::pair<uint32_t, double>> events;                          // (job id, progress) or (job id, 2.0 = completed ok)
+        for (int j = 0; j < J; j++)
+            tsqCompressAsync_MT(c, text.data(), N - 4096 * j, false, &blob[j], &bn[j], false, false, 0,
+                                [&](uint32_t id, bool ok) { std::lock_guard<std::mutex> lk(m); events.push_back({id, ok ? 2.0 : -1.0}); },
+                                [&](uint32_t id, double p) { std::lock_guard<std::mutex> lk(m); events.push_back({id, p}); });
+        tsqDeallocateContextCompression_MT(c);                                    // drains
+        CHECK(events.size() == (size_t)J * (n_blocks + 1));
+        for (int j = 0; j < J; j++)
+            for (size_t e = 0; e <= n_blocks; e++) {
+                const auto& ev = events[(size_t)j * (n_blocks + 1) + e];
+                CHECK(ev.first == (uint32_t)(j + 1));                             // strictly job by job
+                if (e < n_blocks) CHECK(ev.second > (double)e / n_blocks && ev.second <= (double)(e + 1) / n_blocks + 1e-9);
+                else CHECK(ev.second == 2.0);                                     // completion last, after progress reached 1.0
+            }
+        // the same for decompression
+        events.clear();
+        std::vector<uint8_t*> back(J, nullptr);
+        std::vector<size_t> on(J, 0);
+        for (int j = 0; j < J; j++)
+            tsqDecompressAsync_MT(d, blob[j], bn[j], false, &back[j], &on[j], false,
+                                  [&](uint32_t id, bool ok) { std::lock_guard<std::mutex> lk(m); events.push_back({id, ok ? 2.0 : -1.0}); },
+                                  [&](uint32_t id, double p) { std::lock_guard<std::mutex> lk(m); events.push_back({id, p}); });
+        tsqDeallocateContextDecompression_MT(d);
+        CHECK(events.size() == (size_t)J * (n_blocks + 1));
+        for (int j = 0; j < J; j++) {
+            CHECK(events[(size_t)j * (n_blocks + 1) + n_blocks] == std::make_pair((uint32_t)(j + 1), 2.0));
+            CHECK(on[j] == N - 4096 * j && memcmp(back[j], text.data(), on[j]) == 0);
+            free(blob[j]); free(back[j]);
+        }
+    }
+    // ---- tsqDecode with inputSize == 0 (the reference ignores inputSize, tsq_decode.cpp:42-126): the stream is the last thing
+    // in its allocation, so a library that read a worst-case slot from the caller's buffer would run off it
+    {
+        std::vector<uint8_t> in = make_text(70000, 3), comp(90000);
+        TSQCompressionContext* ctx = tsqAllocateContext();
+        uint32_t n = 0, mm = 0;
+        tsqInit(ctx);
+        tsqEncode(ctx, in.data(), comp.data(), &n, 70000, 0);
+        CHECK(n > 0);
+        uint8_t* exact = (uint8_t*)malloc(n);                                     // exactly the stream, nothing behind it
+        memcpy(exact, comp.data(), n);
+        std::vector<uint8_t> out(70000 + 256);
+        tsqDecode(exact, out.data(), &mm, 0, 0);
+        CHECK(mm == 70000 && memcmp(out.data(), in.data(), 70000) == 0);
+        free(exact);
+        tsqDeallocateContext(ctx);
     }
     // ---- FILE* entry points (turbosqueeze.cpp:48-147)
     {
