@@ -398,6 +398,11 @@ def time_e2e(env, ctx, T, wl, lo, n, block, steps):
                 container=pinned_cont, host=host)
 
 
+def byte_sum(torch, t):
+    """Sum of a uint8 tensor's bytes, 64 MiB at a time (sum(dtype=int64) materialises an 8x copy of its input)."""
+    return sum(int(c.sum(dtype=torch.int64).item()) for c in t.split(1 << 26)) if t.numel() else 0
+
+
 def time_gather(env, ctx, wl, res, n, block, nb_total, total_all):
     """N > 1: every rank frames its streams as a TSQ1 body on its GPU, the bodies are gathered into ONE container on
     rank 0 (NCCL over NVLink).  Reported next to `value`, never inside it (the root's NVLink ingress bounds it)."""
@@ -426,7 +431,7 @@ def time_gather(env, ctx, wl, res, n, block, nb_total, total_all):
     mine = int(state["clen"].item()) - 16
     body = env.reduce([float(mine)], "SUM")[0]
     # every rank's body must have arrived: sum of all bytes (the byte-exact check is tests/test_sharded_gpu.py)
-    t = torch.stack([state["cont"][16:16 + mine].sum(dtype=torch.int64)])
+    t = torch.tensor([byte_sum(torch, state["cont"][16:16 + mine])], dtype=torch.int64, device=state["cont"].device)
     if env.world > 1:
         dist.all_reduce(t)
     out = None
@@ -434,7 +439,7 @@ def time_gather(env, ctx, wl, res, n, block, nb_total, total_all):
         hdr = bytes(gathered[:16].cpu().numpy())
         ok = (hdr[:4] == b"TSQ1" and int.from_bytes(hdr[4:8], "little") == nb_total and int.from_bytes(hdr[8:16], "little") == total_all and
               int(gathered.numel()) == 16 + int(body) and bool(torch.equal(gathered[16:16 + mine], state["cont"][16:16 + mine])) and
-              int(gathered[16:].sum(dtype=torch.int64).item()) == int(t[0].item()))
+              byte_sum(torch, gathered[16:]) == int(t[0].item()))
         out = {"ms": round(ms, 3), "container_bytes": int(gathered.numel()), "ok": ok, "root_ingress_gbs": round((body - mine) / (ms * 1e-3) / 1e9, 1),
                "ms_nccl_send_recv": round(times["nccl"], 3), "root_ingress_gbs_nccl_send_recv": round((body - mine) / (times["nccl"] * 1e-3) / 1e9, 1),
                "what": "tsqb_pack_container per rank + one all_gather of the device-side byte counts (one host sync) + every rank writes its "

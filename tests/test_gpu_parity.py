@@ -400,7 +400,8 @@ def test_pipelined_host_path_equals_one_shot(torch, ctx):
 
 
 @pytest.mark.parametrize("kind,block,ext", [("text", 262144, 0), ("random", 262144, 0), ("rep8", 1 << 20, 0), ("text", 4096, 0),
-                                            ("text", 262144, 1), ("rep8", 65536, 1)])
+                                            ("text", 262144, 1), ("rep8", 65536, 1),
+                                            ("text", 65536, 0), ("random", 65536, 0)])     # 4097 blocks: 28 per SM, one decode round above the L1 carve-out
 def test_large_buffers_bit_exact_and_round_trip(torch, ctx, checker, kind, block, ext):
     """BASELINE.json shapes at a size the multi-threaded reference finishes in seconds (256 MiB):
     every stream byte equals the reference's, and decode(encode(x)) == x on the device."""

@@ -93,6 +93,9 @@ constexpr uint32_t kInMask   = kInRing - 1;
 #define TSQB_DEC_WMASK 1           // walker: the 4-group path masks its ring addresses instead of requiring that it does not wrap (with TSQB_DEC_EAGER:
                                    // 2.600 -> 2.560 ms; without the mask the lanes of a walker warp split over two paths: 2.909 ms)
 #endif
+#ifndef TSQB_DEC_ONE_ROUND
+#define TSQB_DEC_ONE_ROUND 1       // a batch of <= 30 blocks per SM is ONE round even when its slots leave the SM 28 KB of L1
+#endif
 constexpr uint32_t kQueue    = TSQB_DEC_QUEUE;       // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
 constexpr uint32_t kPairs    = 16;                   // pairs per copier step (32 symbols)
@@ -1211,8 +1214,11 @@ cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cud
     const size_t slot_bytes = ext ? sizeof(SlotSmem<4096>) : sizeof(SlotSmem<2048>);
     uint32_t cap = kMaxSlots;
     while (slot_bytes * cap > budget) cap--;
-    if (a.ostride >= 65536u) while (cap > 1 && slot_bytes * cap > 195u * 1024u) cap--;
-    if (slot_cap > 0 && cap > (uint32_t)slot_cap) cap = (uint32_t)slot_cap;            // option "decode_slots"
+    if (slot_cap > 0) { if (cap > (uint32_t)slot_cap) cap = (uint32_t)slot_cap; }      // option "decode_slots": explicit, up to what 227 KB hold
+    else if (a.ostride >= 65536u && (ext || per_sm > cap || TSQB_DEC_ONE_ROUND == 0))
+        while (cap > 1 && slot_bytes * cap > 195u * 1024u) cap--;
+    // (27..30 blocks per SM: ONE round above the carve-out beats two rounds of 14..15 slots -- a round cannot be shorter than
+    //  one block's walk: 4096 text blocks of 256 KiB 4.08 -> 3.24 ms, 4440 blocks 4.30 -> 3.40 ms, profiles/r02_experiments.md)
     const uint64_t rounds = (per_sm + cap - 1) / cap;
     uint32_t nslots = (uint32_t)((per_sm + rounds - 1) / rounds);
     if (nslots == 0) nslots = 1;
