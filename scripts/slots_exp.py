@@ -15,7 +15,7 @@ def timeit(fn, reps=5):
     return sorted(ts)[len(ts) // 2]
 
 def main():
-    block = 262144
+    block = int(sys.argv[5]) if len(sys.argv) > 5 else 262144
     nmax = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1600000000
     counts = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [3815, 3848, 4096, 4440, 5000, 6000]
     slot_opts = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0, 26, 28, 30]

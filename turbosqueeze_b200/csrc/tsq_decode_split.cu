@@ -94,7 +94,7 @@ constexpr uint32_t kInMask   = kInRing - 1;
                                    // 2.600 -> 2.560 ms; without the mask the lanes of a walker warp split over two paths: 2.909 ms)
 #endif
 #ifndef TSQB_DEC_ONE_ROUND
-#define TSQB_DEC_ONE_ROUND 1       // a batch of <= 30 blocks per SM is ONE round even when its slots leave the SM 28 KB of L1
+#define TSQB_DEC_ONE_ROUND 1       // batches of 27..30 / 53..60 blocks per SM run as one / two rounds of up to 30 slots (28 KB of L1 left)
 #endif
 constexpr uint32_t kQueue    = TSQB_DEC_QUEUE;       // descriptors per slot
 constexpr uint32_t kQMask    = kQueue - 1;
@@ -1215,10 +1215,16 @@ cudaError_t launch_decode_split(const DecodeArgs& a, bool ext, int sm_count, cud
     uint32_t cap = kMaxSlots;
     while (slot_bytes * cap > budget) cap--;
     if (slot_cap > 0) { if (cap > (uint32_t)slot_cap) cap = (uint32_t)slot_cap; }      // option "decode_slots": explicit, up to what 227 KB hold
-    else if (a.ostride >= 65536u && (ext || per_sm > cap || TSQB_DEC_ONE_ROUND == 0))
-        while (cap > 1 && slot_bytes * cap > 195u * 1024u) cap--;
-    // (27..30 blocks per SM: ONE round above the carve-out beats two rounds of 14..15 slots -- a round cannot be shorter than
-    //  one block's walk: 4096 text blocks of 256 KiB 4.08 -> 3.24 ms, 4440 blocks 4.30 -> 3.40 ms, profiles/r02_experiments.md)
+    else if (a.ostride >= 65536u) {
+        uint32_t lo = cap;
+        while (lo > 1 && slot_bytes * lo > 195u * 1024u) lo--;
+        // A round costs ~(1 + 0.03 x slots) walks of a block, 0.4 more above the carve-out, and never less than one walk: the
+        // slots above the carve-out pay when they save a round out of two or three (27..30 blocks per SM: one round instead of
+        // two, 4096 text blocks of 256 KiB 4.08 -> 3.22 ms; 53..60: two instead of three, 8192 blocks 6.99 -> 6.44 ms) and lose
+        // from there on (32768 blocks: 23.1 vs 25.7 ms).  profiles/r02_experiments.md
+        const uint64_t rounds_hi = (per_sm + cap - 1) / cap, rounds_lo = (per_sm + lo - 1) / lo;
+        if (ext || TSQB_DEC_ONE_ROUND == 0 || !(rounds_hi < rounds_lo && rounds_hi <= 2)) cap = lo;
+    }
     const uint64_t rounds = (per_sm + cap - 1) / cap;
     uint32_t nslots = (uint32_t)((per_sm + rounds - 1) / rounds);
     if (nslots == 0) nslots = 1;
